@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- Jaccard edges/s of the Phenograph graph-weighting path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json `metric`: "Jaccard edges/s at 4M cells k=30"): a synthetic 4M x 30
+planted-cluster kNN index with scrambled cell ids (gficf_b200.synth), E = 1.2e8 edge slots.
+A step is one pass of the hot path over the whole matrix.
+
+  value     whole-job edges/s with the padded int32 index resident in HBM on every GPU;
+            N=1: one launch of the fused kernel; N>1: rows sharded over the ranks (strong
+            scaling: the 4M cells are fixed), per-rank count kernel, NCCL all-gather of the
+            1-byte counts, expand kernel on the host rank
+  e2e       the same metric through the reference-facing call with HOST buffers (pinned):
+            H2D of the f64 R matrix, layout pre-pass, kernel(s), D2H of the (E x 3) doubles
+  roofline  the fused/count kernel against MEASURED_PEAKS.json hbm_gbs, algorithmic bytes
+            (4k+28) per edge
+  cpu_baseline  the reference's own sources (oracle/_ref, unmodified, R runtime stubbed) on a
+            bounded row sample with all host threads
+
+`--impl reference` times only that CPU implementation (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "jaccard_edges_per_s"
+UNIT = "edges/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=4_000_000)
+    ap.add_argument("--k", type=int, default=30)
+    ap.add_argument("--family", default="planted", choices=["planted", "uniform"])
+    ap.add_argument("--no-scramble", action="store_true")
+    ap.add_argument("--seed", type=int, default=180582)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "%dM cells k=%d %s%s kNN index (E=%.3g edge slots)" % (
+        a.cells // 1_000_000, a.k, a.family, "" if a.no_scramble else " scrambled-ids", a.cells * a.k) \
+        if a.cells % 1_000_000 == 0 else "%d cells k=%d %s%s" % (a.cells, a.k, a.family,
+                                                                 "" if a.no_scramble else " scrambled-ids")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons of one GPU sampled with NVML during the timed region."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------- CPU reference
+def reference_sampler(r_matrix, k, budget_s, nthreads=0):
+    """Times the reference's unmodified JCoefficient worker (oracle/_ref) on rows [0,m) gathering
+    from the full matrix; m calibrated so one sample costs about budget_s seconds."""
+    from oracle.binding import Oracle, Reference
+
+    if Reference.available():
+        ref, kind = Reference(), "reference"
+        cores = ref.hw_threads() if nthreads == 0 else nthreads
+
+        def run(lo, hi):
+            ref.parallel_rows(r_matrix, lo, hi, nthreads=nthreads)
+            return ref.last_seconds
+    else:
+        orc, kind = Oracle(), "port"
+        cores = os.cpu_count() or 1
+
+        def run(lo, hi):
+            t0 = time.perf_counter()
+            orc.parallel_rows(r_matrix, lo, hi, nthreads=cores)
+            return time.perf_counter() - t0
+
+    n = r_matrix.shape[0]
+    probe = min(n, 4096 * max(1, cores // 4))
+    t = run(0, probe)
+    rate = probe / max(t, 1e-6)
+    m = int(max(probe, min(n, rate * budget_s)))
+    return run, m, kind, cores
+
+
+def run_reference_arm(a):
+    import numpy as np
+    import torch
+
+    from gficf_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    idx0 = synth.knn_index(a.cells, a.k, family=a.family, seed=a.seed, scramble=not a.no_scramble,
+                           device="cuda" if torch.cuda.is_available() else "cpu")
+    r = synth.to_r_matrix(idx0)
+    del idx0
+    per_step = max(0.5, min(10.0, 150.0 / max(1, a.steps + a.warmup)))
+    run, m, kind, cores = reference_sampler(r, a.k, per_step)
+    for _ in range(a.warmup):
+        run(0, m)
+    times = [run(0, m) for _ in range(a.steps)]
+    tot = float(np.sum(times))
+    val = m * a.k * a.steps / tot
+    sample = "rows [0,%d) of %d (%.3g edges/step) gathering from the full matrix" % (m, a.cells, m * a.k)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import gficf_b200
+    from gficf_b200 import device as D
+    from gficf_b200 import sharding, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    gficf_b200.lib()  # fail loudly now if the extension is missing
+
+    n, k = a.cells, a.k
+    E = n * k
+    bytes_per_edge = 4 * k + 28
+    hbm_peak, peak_src = peaks()
+
+    # ---- inputs: every rank generates the same matrix (counter-based generator)
+    idx0 = synth.knn_index(n, k, family=a.family, seed=a.seed, scramble=not a.no_scramble, device=dev)
+    padded, flags = D.pad_rows(idx0)
+    torch.cuda.synchronize()
+    assert int(flags[0]) == 0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    lo, hi = sharding.slab_bounds(n, world, rank)
+    if world == 1:
+        out = torch.empty((3, E), dtype=torch.float64, device=dev)
+
+        def step():
+            D.jaccard_edges(padded, n, k, out=out, flags=flags)
+        launches_per_step = 1
+    else:
+        counts_local = torch.empty(sharding.slab_rows(n, world) * k, dtype=torch.uint8, device=dev)
+        counts_all = torch.empty(sharding.slab_rows(n, world) * k * world, dtype=torch.uint8, device=dev)
+        out = torch.empty((3, E), dtype=torch.float64, device=dev) if rank == 0 else None
+
+        def step():
+            D.jaccard_counts(padded, n, k, lo, hi, out=counts_local[: (hi - lo) * k], flags=flags)
+            dist.all_gather_into_tensor(counts_all, counts_local)
+            if rank == 0:
+                D.expand(padded, k, counts_all[:E], mode=0, row_lo=0, row_hi=n, out=out)
+        launches_per_step = 2  # count kernel on every rank + expand on the host rank
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+    kev0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+    kev1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for i in range(a.steps):
+        flush.fill_(i & 0xFF)  # evict the index and the previous outputs from L2 (not timed)
+        if world > 1:
+            dist.barrier()
+        ev0[i].record()
+        if world == 1:
+            step()
+        else:
+            kev0[i].record()
+            D.jaccard_counts(padded, n, k, lo, hi, out=counts_local[: (hi - lo) * k], flags=flags)
+            kev1[i].record()
+            dist.all_gather_into_tensor(counts_all, counts_local)
+            if rank == 0:
+                D.expand(padded, k, counts_all[:E], mode=0, row_lo=0, row_hi=n, out=out)
+        ev1[i].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in zip(ev0, ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        kern_ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in zip(kev0, kev1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # max over ranks, per step
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    else:
+        kern_ms = step_ms
+    assert int(flags[0]) == 0, "fast kernel flagged the synthetic input"
+    total_ms = float(step_ms.sum())
+    ms_per_step = total_ms / a.steps
+    value = E / (ms_per_step * 1e-3)
+    kern_avg_ms = float(kern_ms.mean())
+    edges_per_launch = E if world == 1 else sharding.slab_rows(n, world) * k
+    bpe = bytes_per_edge if world == 1 else (4 * k + 4 + 1)  # count kernel writes 1 B/edge
+    achieved = edges_per_launch * bpe / (kern_avg_ms * 1e-3) / 1e9
+
+    # ---- end to end through the reference-facing call, host buffers (pinned)
+    e2e = None
+    if not a.no_e2e:
+        e2e_steps = a.e2e_steps or min(a.steps, 10)
+        if world == 1:
+            r_host = gficf_b200.pinned_empty((n, k))
+            r_host[...] = synth.to_r_matrix(idx0)
+            out_host = gficf_b200.pinned_empty((E, 3))
+            for _ in range(2):
+                gficf_b200.rcpp_parallel_jaccard_coef(r_host, False, 1, out=out_host)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                gficf_b200.rcpp_parallel_jaccard_coef(r_host, False, 1, out=out_host)
+            dt = (time.perf_counter() - t0) / e2e_steps
+            tm = gficf_b200.last_timings()
+            e2e = {"value": E / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": 24 * E,
+                   "ms_per_step": dt * 1e3, "call": "gficf_b200.rcpp_parallel_jaccard_coef (pinned host buffers)",
+                   "breakdown_ms": {kk: round(v, 3) for kk, v in tm.items() if kk != "reserved"}}
+        else:
+            r_host = out_host = None
+            if rank == 0:
+                r_host = gficf_b200.pinned_empty((n, k))
+                r_host[...] = synth.to_r_matrix(idx0)
+                out_host = gficf_b200.pinned_empty((E, 3))
+            for _ in range(2):
+                sharding.rcpp_parallel_jaccard_coef_sharded(r_host, n, k, out=out_host)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                sharding.rcpp_parallel_jaccard_coef_sharded(r_host, n, k, out=out_host)
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            e2e = {"value": E / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": 8 * E,
+                   "d2h_bytes_per_step": 24 * E, "ms_per_step": float(dt[0]) * 1e3,
+                   "call": "gficf_b200.sharding.rcpp_parallel_jaccard_coef_sharded (host rank 0, pinned)"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        r = synth.to_r_matrix(idx0)
+        run, m, kind, cores = reference_sampler(r, k, a.cpu_seconds)
+        t = run(0, m)
+        cpu = {"value": m * k / t, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "rows [0,%d) of %d (%.3g edges) gathering from the full matrix, %.1f s" % (m, n, m * k, t)}
+        # and the GPU result of those rows must be what the reference computed
+        ref_rows = min(m, 2000)
+        from oracle.binding import Reference, Oracle
+        chk = (Reference() if Reference.available() else Oracle()).parallel_rows(r, 0, ref_rows)
+        got = out[:, : ref_rows * k].cpu().numpy().T
+        cpu["gpu_matches_on_sample"] = bool(np.array_equal(got, chk))
+
+    if rank == 0:
+        g, b, s, v = (C_int32() for _ in range(4))
+        gficf_b200.lib().gficf_cuda_last_launch(g, b, s, v)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32 ids / f64 weights", "data": "synthetic",
+            "config": {"workload": workload_name(a), "cells": n, "k": k, "edges": E,
+                       "l2": "explicit 256 MiB flush write between timed steps; index 4*n*32 B = %.0f MB > 126 MB L2"
+                             % (n * 32 * 4 / 1e6),
+                       "sharding": "none" if world == 1 else
+                       "rows/%d; resident replicated int32 index; u8 count all-gather; expand on rank 0" % world,
+                       "launch": {"grid": g.value, "block": b.value, "smem": s.value}},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "kernel": "jaccard_small_k_kernel<32,false>" if world == 1 and k <= 32 and k > 16 else "jaccard kernel",
+                         "bytes_per_edge": bpe, "edges_per_launch": edges_per_launch,
+                         "kernel_ms": kern_avg_ms, "peak_source": peak_src},
+            "clocks": clocks, "gpu_launches": launches_per_step * a.steps,
+            "loop_wall_ms": t_wall * 1e3,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def C_int32():
+    import ctypes
+
+    return ctypes.c_int32(0)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,828 @@
+// gficf_cuda.cu -- C ABI (include/gficf_cuda.h) and host orchestration of the
+// B200-native Jaccard path: device workspaces, H2D / D2H pipelines, kernel
+// dispatch, multi-GPU row sharding over NCCL.
+//
+// Replaces the bodies of rcpp_parallel_jaccard_coef
+// (reference src/rcpp_parallel_jaccard_coeff.cpp:58-80) and jaccard_coeff
+// (src/jaccard_coeff.cpp:19-45).  There is deliberately no CPU fallback.
+#include "../../include/gficf_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "jaccard_kernels.cuh"
+#include "nccl_dyn.h"
+
+namespace {
+
+using namespace gficf;
+
+// ------------------------------------------------------------------ errors
+struct Err {
+  int code = GFICF_OK;
+  std::string msg;
+};
+
+void set_err(char* err, size_t errlen, const std::string& m) {
+  if (err && errlen) {
+    snprintf(err, errlen, "%s", m.c_str());
+  }
+}
+
+std::string fmt(const char* f, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof buf, f, ap);
+  va_end(ap);
+  return buf;
+}
+
+#define CU_TRY(expr)                                                                   \
+  do {                                                                                 \
+    cudaError_t e_ = (expr);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      throw Err{GFICF_E_CUDA, fmt("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                  __FILE__, __LINE__)};                                \
+    }                                                                                  \
+  } while (0)
+
+#define NCCL_TRY(expr)                                                                   \
+  do {                                                                                   \
+    ncclResult_t r_ = (expr);                                                            \
+    if (r_ != ncclSuccess) {                                                             \
+      throw Err{GFICF_E_NCCL, fmt("%s failed: %s (%s:%d)", #expr,                        \
+                                  nccl_dyn::get().GetErrorString(r_), __FILE__, __LINE__)}; \
+    }                                                                                    \
+  } while (0)
+
+// ------------------------------------------------------------------ launch bookkeeping
+struct LaunchInfo {
+  int grid = 0, block = 0, smem = 0, variant = 0;
+};
+thread_local LaunchInfo tl_launch;
+thread_local double tl_timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+struct DevProps {
+  bool ok = false;
+  int sms = 0;
+};
+DevProps g_props[64];
+std::mutex g_mu;
+
+int sm_count() {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (dev < 64 && g_props[dev].ok) return g_props[dev].sms;
+  int sms = 0;
+  CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 64) g_props[dev] = {true, sms};
+  return sms;
+}
+
+int32_t row_stride(int32_t k) {
+  if (k <= 4) return 4;
+  if (k <= 8) return 8;
+  if (k <= 16) return 16;
+  if (k <= 32) return 32;
+  return (k + 7) / 8 * 8;
+}
+
+int wide_log_ts(int k) { return k <= 48 ? 10 : (k <= 64 ? 11 : 12); }
+
+size_t wide_smem_bytes(int log_ts) {
+  return (size_t)kWideWarps * ((1u << log_ts) + 256) * 4 + 129 * sizeof(double);
+}
+
+// persistent grid: resident CTAs per SM x SM count, capped by the work
+template <typename K>
+int persistent_grid(K kernel, int block, size_t smem, long long work_ctas) {
+  int per_sm = 0;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long g = (long long)per_sm * sm_count();
+  if (g > work_ctas) g = work_ctas;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <int KP, bool CO>
+void launch_small(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
+                  uint8_t* u, unsigned* flags, cudaStream_t st) {
+  auto kern = jaccard_small_k_kernel<KP, CO>;
+  const int block = kSmallWarps * 32;
+  const int grid = persistent_grid(kern, block, 0, (hi - lo + kSmallWarps - 1) / kSmallWarps);
+  kern<<<grid, block, 0, st>>>(idx, k, lo, hi, f, t, w, u, flags);
+  tl_launch = {grid, block, (int)(sizeof(unsigned) * kSmallWarps * SmallK<KP>::TS + 33 * 8), KP};
+}
+
+template <int LOG_TS, bool CO>
+void launch_wide(const int* idx, int k, int kp, long long lo, long long hi, double* f, double* t,
+                 double* w, uint8_t* u, unsigned* flags, cudaStream_t st) {
+  auto kern = jaccard_wide_k_kernel<LOG_TS, CO>;
+  const size_t smem = wide_smem_bytes(LOG_TS);
+  static thread_local bool attr_set[64] = {};
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev & 63] = true;
+  }
+  const int block = kWideWarps * 32;
+  const int grid = persistent_grid(kern, block, smem, (hi - lo + kWideWarps - 1) / kWideWarps);
+  kern<<<grid, block, smem, st>>>(idx, k, kp, lo, hi, f, t, w, u, flags);
+  tl_launch = {grid, block, (int)smem, 1000 + LOG_TS};
+}
+
+// fast kernels; returns false when k is outside their range
+template <bool CO>
+bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
+                 uint8_t* u, unsigned* flags, cudaStream_t st) {
+  if (hi <= lo) return true;
+  const int kp = row_stride(k);
+  if (k <= 4) launch_small<4, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
+  else if (k <= 8) launch_small<8, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
+  else if (k <= 16) launch_small<16, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
+  else if (k <= 32) launch_small<32, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
+  else if (k <= 128) {
+    switch (wide_log_ts(k)) {
+      case 10: launch_wide<10, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
+      case 11: launch_wide<11, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
+      default: launch_wide<12, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
+    }
+  } else {
+    return false;
+  }
+  CU_TRY(cudaGetLastError());
+  return true;
+}
+
+int grid_1d(long long total, int block, int cap_per_sm = 8) {
+  long long g = (total + block - 1) / block;
+  long long cap = (long long)sm_count() * cap_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+void launch_layout(const double* src, long long ld_rows, long long ld_row0, long long n, int k,
+                   long long lo, long long hi, int* dst, unsigned* flags, cudaStream_t st) {
+  if (hi <= lo) return;
+  const int kp = row_stride(k);
+  const size_t smem = (size_t)kLayoutTileR * (kp + 1) * sizeof(int);
+  if (smem > 48 * 1024) {
+    static thread_local bool attr_set[64] = {};
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+      CU_TRY(cudaFuncSetAttribute(layout_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  200 * 1024));
+      attr_set[dev & 63] = true;
+    }
+    if (smem > 200 * 1024) throw Err{GFICF_E_LIMIT, "k too large for the layout pre-pass tile"};
+  }
+  const long long ntiles = (hi - lo + kLayoutTileR - 1) / kLayoutTileR;
+  long long g = std::min<long long>(ntiles, (long long)sm_count() * 8);
+  layout_f64_kernel<<<(int)g, kLayoutThreads, smem, st>>>(src, ld_rows, ld_row0, n, k, kp, lo, hi, dst,
+                                                          flags);
+  CU_TRY(cudaGetLastError());
+}
+
+void launch_exact(const int* idx, int k, long long lo, long long hi, int set_sem, void* d_u,
+                  cudaStream_t st) {
+  if (hi <= lo) return;
+  const int kp = row_stride(k);
+  const long long total = (hi - lo) * (long long)k;
+  const int grid = grid_1d(total, 128, 16);
+  if (k <= 255)
+    jaccard_exact_kernel<uint8_t><<<grid, 128, 0, st>>>(idx, k, kp, lo, hi, set_sem, (uint8_t*)d_u);
+  else
+    jaccard_exact_kernel<uint16_t><<<grid, 128, 0, st>>>(idx, k, kp, lo, hi, set_sem, (uint16_t*)d_u);
+  CU_TRY(cudaGetLastError());
+}
+
+size_t expand_scratch_bytes(long long slab_e) {
+  const long long nchunks = (slab_e + kCompactChunk - 1) / kCompactChunk;
+  return (size_t)(nchunks + 1) * sizeof(long long);
+}
+
+template <typename CT>
+void launch_expand_t(const int* idx, int k, long long lo, long long hi, const CT* d_u, int mode,
+                     double* f, double* t, double* w, void* scratch, long long* d_nw,
+                     cudaStream_t st) {
+  const int kp = row_stride(k);
+  const long long total = (hi - lo) * (long long)k;
+  if (total <= 0) return;
+  if (mode == GFICF_MODE_PARALLEL) {
+    expand_fixed_kernel<CT><<<grid_1d(total, 256, 8), 256, 0, st>>>(idx, k, kp, lo, hi, d_u, f, t, w);
+  } else {
+    long long* chunk = (long long*)scratch;
+    const long long nchunks = (total + kCompactChunk - 1) / kCompactChunk;
+    if (nchunks > 0x7fffffffLL) throw Err{GFICF_E_LIMIT, "slab too large for compaction"};
+    compact_count_kernel<CT><<<(int)nchunks, kCompactThreads, 0, st>>>(d_u, total, chunk);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(chunk, nchunks, d_nw);
+    compact_scatter_kernel<CT><<<(int)nchunks, kCompactThreads, 0, st>>>(idx, k, kp, lo, d_u, total,
+                                                                        chunk, f, t, w);
+    zero_tail_kernel<<<grid_1d(total, 256, 8), 256, 0, st>>>(d_nw, total, f, t, w);
+  }
+  CU_TRY(cudaGetLastError());
+}
+
+void launch_expand(const int* idx, int k, long long lo, long long hi, const void* d_u, int mode,
+                   double* f, double* t, double* w, void* scratch, long long* d_nw, cudaStream_t st) {
+  if (k <= 255)
+    launch_expand_t<uint8_t>(idx, k, lo, hi, (const uint8_t*)d_u, mode, f, t, w, scratch, d_nw, st);
+  else
+    launch_expand_t<uint16_t>(idx, k, lo, hi, (const uint16_t*)d_u, mode, f, t, w, scratch, d_nw, st);
+}
+
+// ------------------------------------------------------------------ per-device workspace
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void need(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) CU_TRY(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    CU_TRY(cudaMalloc(&p, bytes));
+    cap = bytes;
+  }
+  void drop() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void need(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) CU_TRY(cudaFreeHost(p));
+    p = nullptr;
+    cap = 0;
+    CU_TRY(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    cap = bytes;
+  }
+  void drop() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+constexpr int kMaxChunks = 32;
+constexpr size_t kStageBytes = 32u << 20;  // pinned bounce buffer (x2 per direction)
+
+struct DeviceWs {
+  int dev = -1;
+  bool init = false;
+  cudaStream_t s_comp = nullptr, s_copy = nullptr;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_chunk[kMaxChunks] = {};
+  cudaEvent_t ev_k0[kMaxChunks] = {}, ev_k1[kMaxChunks] = {};
+  Buf in_f64, idx, out, counts, scratch, small;  // small: flags (4B) + n_written (8B)
+  PinBuf stage[2];
+  cudaEvent_t ev_stage[2] = {};
+  unsigned* h_small = nullptr;  // pinned mirror of `small`
+
+  void ensure(int d) {
+    if (init) return;
+    dev = d;
+    CU_TRY(cudaSetDevice(dev));
+    CU_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
+    for (auto& e : ev_chunk) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ev_k0) CU_TRY(cudaEventCreate(&e));
+    for (auto& e : ev_k1) CU_TRY(cudaEventCreate(&e));
+    for (auto& e : ev_stage) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    small.need(64);
+    CU_TRY(cudaHostAlloc((void**)&h_small, 64, cudaHostAllocDefault));
+    init = true;
+  }
+  void release() {
+    if (!init) return;
+    cudaSetDevice(dev);
+    cudaDeviceSynchronize();
+    in_f64.drop(); idx.drop(); out.drop(); counts.drop(); scratch.drop(); small.drop();
+    stage[0].drop(); stage[1].drop();
+    if (h_small) cudaFreeHost(h_small);
+    h_small = nullptr;
+    for (auto& e : ev) cudaEventDestroy(e);
+    for (auto& e : ev_chunk) cudaEventDestroy(e);
+    for (auto& e : ev_k0) cudaEventDestroy(e);
+    for (auto& e : ev_k1) cudaEventDestroy(e);
+    for (auto& e : ev_stage) cudaEventDestroy(e);
+    cudaStreamDestroy(s_comp);
+    cudaStreamDestroy(s_copy);
+    init = false;
+  }
+};
+
+constexpr int kMaxDevices = 16;
+DeviceWs g_ws[kMaxDevices];
+std::mutex g_call_mu;  // one host-level call at a time (workspaces are shared)
+int g_default_devices = -1;
+
+struct NcclState {
+  int ndev = 0;
+  ncclComm_t comms[kMaxDevices] = {};
+} g_nccl;
+
+void nccl_release() {
+  if (g_nccl.ndev) {
+    for (int i = 0; i < g_nccl.ndev; ++i)
+      if (g_nccl.comms[i]) nccl_dyn::get().CommDestroy(g_nccl.comms[i]);
+    g_nccl = NcclState();
+  }
+}
+
+void nccl_ensure(int ndev) {
+  if (g_nccl.ndev == ndev) return;
+  nccl_release();
+  if (!nccl_dyn::get().ok) throw Err{GFICF_E_NCCL, "cannot load libnccl.so.2: " + nccl_dyn::get().why};
+  int devs[kMaxDevices];
+  for (int i = 0; i < ndev; ++i) devs[i] = i;
+  NCCL_TRY(nccl_dyn::get().CommInitAll(g_nccl.comms, ndev, devs));
+  g_nccl.ndev = ndev;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Host -> device of a strided 2-D block (rows x cols doubles, source leading
+// dimension ld_src, destination dense with leading dimension rows).  Pinned
+// sources go straight to the copy engine; pageable ones are staged through two
+// pinned bounce buffers so the host memcpy overlaps the DMA.
+void h2d_block(DeviceWs& ws, const double* src, long long ld_src, double* dst, long long rows,
+               int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return;
+  if (is_pinned(src)) {
+    CU_TRY(cudaMemcpy2DAsync(dst, rows * sizeof(double), src, ld_src * sizeof(double),
+                             rows * sizeof(double), cols, cudaMemcpyHostToDevice, st));
+    return;
+  }
+  ws.stage[0].need(kStageBytes);
+  ws.stage[1].need(kStageBytes);
+  const long long per = kStageBytes / sizeof(double);
+  int b = 0;
+  for (int c = 0; c < cols; ++c) {
+    for (long long r0 = 0; r0 < rows; r0 += per) {
+      const long long m = std::min(per, rows - r0);
+      CU_TRY(cudaEventSynchronize(ws.ev_stage[b]));
+      memcpy(ws.stage[b].p, src + (long long)c * ld_src + r0, m * sizeof(double));
+      CU_TRY(cudaMemcpyAsync(dst + (long long)c * rows + r0, ws.stage[b].p, m * sizeof(double),
+                             cudaMemcpyHostToDevice, st));
+      CU_TRY(cudaEventRecord(ws.ev_stage[b], st));
+      b ^= 1;
+    }
+  }
+}
+
+// Device -> host of a contiguous run.  Pageable destinations are staged.
+void d2h_run(DeviceWs& ws, double* dst, const double* src, long long count, cudaStream_t st) {
+  if (count <= 0) return;
+  if (is_pinned(dst)) {
+    CU_TRY(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return;
+  }
+  ws.stage[0].need(kStageBytes);
+  ws.stage[1].need(kStageBytes);
+  const long long per = kStageBytes / sizeof(double);
+  // two-deep pipeline: DMA chunk c+1 into one bounce buffer while memcpy-ing chunk c out
+  long long pend_off[2] = {-1, -1}, pend_cnt[2] = {0, 0};
+  int b = 0;
+  for (long long off = 0; off < count; off += per) {
+    const long long m = std::min(per, count - off);
+    if (pend_off[b] >= 0) {
+      CU_TRY(cudaEventSynchronize(ws.ev_stage[b]));
+      memcpy(dst + pend_off[b], ws.stage[b].p, pend_cnt[b] * sizeof(double));
+    }
+    CU_TRY(cudaMemcpyAsync(ws.stage[b].p, src + off, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(ws.ev_stage[b], st));
+    pend_off[b] = off;
+    pend_cnt[b] = m;
+    b ^= 1;
+  }
+  for (int q = 0; q < 2; ++q) {
+    if (pend_off[b] >= 0) {
+      CU_TRY(cudaEventSynchronize(ws.ev_stage[b]));
+      memcpy(dst + pend_off[b], ws.stage[b].p, pend_cnt[b] * sizeof(double));
+      pend_off[b] = -1;
+    }
+    b ^= 1;
+  }
+}
+
+struct SlabResult {
+  unsigned flags = 0;
+  long long n_written = 0;
+  float ms_h2d = 0, ms_k0 = 0, ms_k1 = 0, ms_d2h = 0, ms_gather = 0;
+  int launches = 0;
+  Err err;
+};
+
+// One device's share of a call: rows [lo,hi) of n.  With ndev>1 the int32 index
+// slabs are exchanged with an in-place NCCL all-gather.
+void run_device(int rank, int ndev, const double* h_idx, long long n, int k, long long rows_per,
+                double* h_out, int mode, SlabResult* res) {
+  try {
+    DeviceWs& ws = g_ws[rank];
+    CU_TRY(cudaSetDevice(rank));
+    ws.ensure(rank);
+    const int kp = row_stride(k);
+    const long long lo = std::min<long long>(n, rank * rows_per);
+    const long long hi = std::min<long long>(n, lo + rows_per);
+    const long long rows = hi - lo;
+    const long long E = n * (long long)k;
+    const long long slab_e = rows * (long long)k;
+    const int cbytes = k <= 255 ? 1 : 2;
+
+    ws.in_f64.need(std::max<size_t>(16, (size_t)rows * k * sizeof(double)));
+    ws.idx.need(std::max<size_t>(16, (size_t)rows_per * ndev * kp * sizeof(int)));
+    unsigned* d_flags = (unsigned*)ws.small.p;
+    long long* d_nw = (long long*)((char*)ws.small.p + 8);
+    CU_TRY(cudaMemsetAsync(ws.small.p, 0, 64, ws.s_comp));
+
+    // ---- H2D of this device's rows (all k columns), layout pre-pass
+    CU_TRY(cudaEventRecord(ws.ev[0], ws.s_comp));
+    h2d_block(ws, h_idx + lo, n, (double*)ws.in_f64.p, rows, k, ws.s_comp);
+    CU_TRY(cudaEventRecord(ws.ev[1], ws.s_comp));
+    launch_layout((const double*)ws.in_f64.p, rows, lo, n, k, lo, hi, (int*)ws.idx.p, d_flags,
+                  ws.s_comp);
+    res->launches += rows > 0;
+    CU_TRY(cudaEventRecord(ws.ev[2], ws.s_comp));
+    // ---- exchange index slabs
+    if (ndev > 1) {
+      const size_t cnt = (size_t)rows_per * kp;
+      NCCL_TRY(nccl_dyn::get().AllGather((const char*)ws.idx.p + (size_t)rank * cnt * sizeof(int),
+                                         ws.idx.p, cnt, ncclInt32, g_nccl.comms[rank], ws.s_comp));
+    }
+    CU_TRY(cudaEventRecord(ws.ev[3], ws.s_comp));
+
+    const int* d_idx = (const int*)ws.idx.p;
+    const bool fast_ok = k <= 128;
+    ws.out.need(std::max<size_t>(16, (size_t)slab_e * 3 * sizeof(double)));
+    double* d_from = (double*)ws.out.p;
+    double* d_to = d_from + slab_e;
+    double* d_w = d_to + slab_e;
+    auto read_small = [&]() {
+      CU_TRY(cudaMemcpyAsync(ws.h_small, ws.small.p, 16, cudaMemcpyDeviceToHost, ws.s_comp));
+      CU_TRY(cudaStreamSynchronize(ws.s_comp));
+      res->flags |= ws.h_small[0];
+    };
+    auto front_timings = [&]() {
+      CU_TRY(cudaEventElapsedTime(&res->ms_h2d, ws.ev[0], ws.ev[1]));
+      CU_TRY(cudaEventElapsedTime(&res->ms_k0, ws.ev[1], ws.ev[2]));
+      CU_TRY(cudaEventElapsedTime(&res->ms_gather, ws.ev[2], ws.ev[3]));
+    };
+    res->n_written = -1;
+
+    if (mode == GFICF_MODE_PARALLEL && fast_ok) {
+      // fused kernel in row chunks; the D2H of chunk c overlaps the kernel of chunk c+1
+      const int nch =
+          (int)std::min<long long>(kMaxChunks, std::max<long long>(1, slab_e * 24 / (48ll << 20)));
+      const long long rpc = (rows + nch - 1) / nch;
+      int used = 0;
+      for (int c = 0; c < nch; ++c) {
+        const long long clo = lo + c * rpc, chi = std::min(hi, clo + rpc);
+        if (clo >= chi) break;
+        const long long eo = (clo - lo) * k;
+        CU_TRY(cudaEventRecord(ws.ev_k0[c], ws.s_comp));
+        launch_fast<false>(d_idx, k, clo, chi, d_from + eo, d_to + eo, d_w + eo, nullptr, d_flags,
+                           ws.s_comp);
+        CU_TRY(cudaEventRecord(ws.ev_k1[c], ws.s_comp));
+        CU_TRY(cudaEventRecord(ws.ev_chunk[c], ws.s_comp));
+        res->launches++;
+        used = c + 1;
+      }
+      CU_TRY(cudaStreamWaitEvent(ws.s_copy, ws.ev[3], 0));
+      CU_TRY(cudaEventRecord(ws.ev[4], ws.s_copy));
+      for (int c = 0; c < used; ++c) {
+        const long long clo = lo + c * rpc, chi = std::min(hi, clo + rpc);
+        const long long eo = (clo - lo) * k, ce = (chi - clo) * k;
+        CU_TRY(cudaStreamWaitEvent(ws.s_copy, ws.ev_chunk[c], 0));
+        d2h_run(ws, h_out + lo * k + eo, d_from + eo, ce, ws.s_copy);
+        d2h_run(ws, h_out + E + lo * k + eo, d_to + eo, ce, ws.s_copy);
+        d2h_run(ws, h_out + 2 * E + lo * k + eo, d_w + eo, ce, ws.s_copy);
+      }
+      CU_TRY(cudaEventRecord(ws.ev[5], ws.s_copy));
+      read_small();
+      CU_TRY(cudaStreamSynchronize(ws.s_copy));
+      front_timings();
+      for (int c = 0; c < used; ++c) {
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, ws.ev_k0[c], ws.ev_k1[c]));
+        res->ms_k1 += ms;
+      }
+      CU_TRY(cudaEventElapsedTime(&res->ms_d2h, ws.ev[4], ws.ev[5]));
+      if (res->flags & kFlagBadId) return;  // the caller reports GFICF_E_RANGE
+      if (!(res->flags & (kFlagDupId | kFlagHashFail))) return;
+      // a row repeats an id (or found no collision-free hash): redo with the exact kernel
+    } else {
+      read_small();
+      front_timings();
+      if (res->flags & kFlagBadId) return;
+    }
+
+    // ---- counts -> expand path: the serial export, k>128, or rows with repeated ids
+    ws.counts.need(std::max<size_t>(16, (size_t)slab_e * cbytes));
+    ws.scratch.need(expand_scratch_bytes(slab_e));
+    CU_TRY(cudaEventRecord(ws.ev[6], ws.s_comp));
+    bool exact = !fast_ok || (res->flags & (kFlagDupId | kFlagHashFail));
+    if (!exact) {
+      launch_fast<true>(d_idx, k, lo, hi, nullptr, nullptr, nullptr, (uint8_t*)ws.counts.p, d_flags,
+                        ws.s_comp);
+      res->launches++;
+      read_small();
+      exact = (res->flags & (kFlagDupId | kFlagHashFail)) != 0;
+    }
+    if (exact) {
+      launch_exact(d_idx, k, lo, hi, mode == GFICF_MODE_SERIAL ? 1 : 0, ws.counts.p, ws.s_comp);
+      res->launches++;
+    }
+    launch_expand(d_idx, k, lo, hi, ws.counts.p, mode, d_from, d_to, d_w, ws.scratch.p, d_nw,
+                  ws.s_comp);
+    res->launches += mode == GFICF_MODE_SERIAL ? 4 : 1;
+    CU_TRY(cudaEventRecord(ws.ev[7], ws.s_comp));
+    read_small();
+    if (mode == GFICF_MODE_SERIAL) res->n_written = *(long long*)((char*)ws.h_small + 8);
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, ws.ev[6], ws.ev[7]));
+    res->ms_k1 += ms;
+    CU_TRY(cudaEventRecord(ws.ev[4], ws.s_copy));
+    d2h_run(ws, h_out + lo * k, d_from, slab_e, ws.s_copy);
+    d2h_run(ws, h_out + E + lo * k, d_to, slab_e, ws.s_copy);
+    d2h_run(ws, h_out + 2 * E + lo * k, d_w, slab_e, ws.s_copy);
+    CU_TRY(cudaEventRecord(ws.ev[5], ws.s_copy));
+    CU_TRY(cudaStreamSynchronize(ws.s_copy));
+    float ms2 = 0;
+    CU_TRY(cudaEventElapsedTime(&ms2, ws.ev[4], ws.ev[5]));
+    res->ms_d2h += ms2;
+  } catch (const Err& e) {
+    res->err = e;
+  }
+}
+
+int visible_devices() {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return c;
+}
+
+int default_devices() {
+  if (g_default_devices < 0) {
+    const char* e = getenv("GFICF_CUDA_DEVICES");
+    int v = e ? atoi(e) : 1;
+    g_default_devices = v >= 1 ? v : 1;
+  }
+  return g_default_devices;
+}
+
+}  // namespace
+
+// ============================================================================
+// C ABI
+// ============================================================================
+#define API_BEGIN try {
+#define API_END                                \
+  }                                            \
+  catch (const Err& e) {                       \
+    set_err(err, errlen, e.msg);               \
+    return e.code;                             \
+  }                                            \
+  catch (const std::exception& e) {            \
+    set_err(err, errlen, e.what());            \
+    return GFICF_E_CUDA;                       \
+  }                                            \
+  catch (...) {                                \
+    set_err(err, errlen, "unknown failure");   \
+    return GFICF_E_CUDA;                       \
+  }
+
+extern "C" {
+
+const char* gficf_cuda_version(void) { return "gficf_cuda 0.1 (sm_100a; CUDA " __DATE__ ")"; }
+
+int32_t gficf_cuda_row_stride(int32_t k) { return k < 1 ? 0 : row_stride(k); }
+
+int gficf_cuda_device_count(void) { return visible_devices(); }
+
+int gficf_cuda_set_devices(int32_t n_devices) {
+  if (n_devices < 1 || n_devices > kMaxDevices) return GFICF_E_ARG;
+  g_default_devices = n_devices;
+  return GFICF_OK;
+}
+
+int gficf_cuda_get_devices(void) { return default_devices(); }
+
+int gficf_cuda_host_alloc(void** p, size_t bytes) {
+  if (!p) return GFICF_E_ARG;
+  *p = nullptr;
+  if (cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return GFICF_E_CUDA;
+  }
+  return GFICF_OK;
+}
+
+int gficf_cuda_host_free(void* p) {
+  if (!p) return GFICF_OK;
+  if (cudaFreeHost(p) != cudaSuccess) {
+    cudaGetLastError();
+    return GFICF_E_CUDA;
+  }
+  return GFICF_OK;
+}
+
+int gficf_cuda_release(void) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  nccl_release();
+  for (auto& w : g_ws) w.release();
+  return GFICF_OK;
+}
+
+int gficf_cuda_last_timings(double* ms8) {
+  if (!ms8) return GFICF_E_ARG;
+  memcpy(ms8, tl_timings, sizeof tl_timings);
+  return GFICF_OK;
+}
+
+int gficf_cuda_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* variant) {
+  if (grid) *grid = tl_launch.grid;
+  if (block) *block = tl_launch.block;
+  if (smem_bytes) *smem_bytes = tl_launch.smem;
+  if (variant) *variant = tl_launch.variant;
+  return GFICF_OK;
+}
+
+int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int32_t n_devices,
+                       int32_t mode, int64_t* n_written, char* err, size_t errlen) {
+  API_BEGIN
+  if (err && errlen) err[0] = 0;
+  if (n < 0 || k < 0) throw Err{GFICF_E_ARG, "negative matrix dimension"};
+  if (mode != GFICF_MODE_PARALLEL && mode != GFICF_MODE_SERIAL)
+    throw Err{GFICF_E_ARG, "mode must be 0 (parallel, fixed slots) or 1 (serial, compacted)"};
+  if (n_written) *n_written = 0;
+  if (n == 0 || k == 0) return GFICF_OK;
+  if (!idx || !out) throw Err{GFICF_E_ARG, "null matrix pointer"};
+  // the reference holds rows and nrow*ncol in `int` (rcpp_parallel_jaccard_coeff.cpp:28,67)
+  if (n >= 0x7fffffffLL - 2 || (long double)n * k >= 2147483647.0L)
+    throw Err{GFICF_E_LIMIT, "n*k must stay below 2^31 (the reference's int row index)"};
+  if (k > 65535) throw Err{GFICF_E_LIMIT, "k above 65535 is not supported"};
+  int ndev = n_devices > 0 ? n_devices : default_devices();
+  const int vis = visible_devices();
+  if (vis < 1) throw Err{GFICF_E_CUDA, "no CUDA device is visible (this path has no CPU fallback)"};
+  if (ndev > vis)
+    throw Err{GFICF_E_ARG, fmt("%d devices requested but only %d visible", ndev, vis)};
+  if (ndev > kMaxDevices) throw Err{GFICF_E_ARG, "too many devices"};
+  if (mode == GFICF_MODE_SERIAL) ndev = 1;  // global row compaction: one device
+  if ((long long)ndev > n) ndev = 1;
+
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  const auto t0 = std::chrono::steady_clock::now();
+  const long long rows_per = (n + ndev - 1) / ndev;
+  std::vector<SlabResult> res(ndev);
+  if (ndev == 1) {
+    run_device(0, 1, idx, n, k, rows_per, out, mode, &res[0]);
+  } else {
+    nccl_ensure(ndev);
+    std::vector<std::thread> th;
+    for (int r = 0; r < ndev; ++r)
+      th.emplace_back(run_device, r, ndev, idx, (long long)n, (int)k, rows_per, out, (int)mode, &res[r]);
+    for (auto& t : th) t.join();
+  }
+  cudaSetDevice(prev_dev);
+  const auto t1 = std::chrono::steady_clock::now();
+  unsigned flags = 0;
+  double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (auto& r : res) {
+    if (r.err.code != GFICF_OK) throw r.err;
+    flags |= r.flags;
+    tm[0] = std::max<double>(tm[0], r.ms_h2d);
+    tm[1] = std::max<double>(tm[1], r.ms_k0);
+    tm[2] = std::max<double>(tm[2], r.ms_k1);
+    tm[3] = std::max<double>(tm[3], r.ms_d2h);
+    tm[5] = std::max<double>(tm[5], r.ms_gather);
+    tm[6] += r.launches;
+  }
+  tm[4] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  memcpy(tl_timings, tm, sizeof tm);
+  if (flags & kFlagBadId)
+    throw Err{GFICF_E_RANGE,
+              "neighbour ids must be integers in [1, nrow] (NaN, fractional or out-of-range id found)"};
+  if (n_written) *n_written = res[0].n_written;
+  return GFICF_OK;
+  API_END
+}
+
+// ---------------------------------------------------------------- device-buffer entries
+#define DEV_BEGIN      \
+  char* err = nullptr; \
+  size_t errlen = 0;   \
+  API_BEGIN
+#define DEV_END API_END
+
+int gficf_cuda_layout_dev(const double* d_idx_f64, int64_t ld_rows, int64_t ld_row0, int64_t n,
+                          int32_t k, int64_t row_lo, int64_t row_hi, int32_t* d_idx_i32,
+                          uint32_t* d_flags, void* stream) {
+  DEV_BEGIN
+  if (!d_idx_f64 || !d_idx_i32 || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
+  launch_layout(d_idx_f64, ld_rows, ld_row0, n, k, row_lo, row_hi, d_idx_i32, d_flags,
+                (cudaStream_t)stream);
+  return GFICF_OK;
+  DEV_END
+}
+
+int gficf_cuda_pad_dev(const int32_t* d_idx_dense, int64_t n, int32_t k, int64_t row_lo,
+                       int64_t row_hi, int32_t* d_idx_i32, uint32_t* d_flags, void* stream) {
+  DEV_BEGIN
+  if (!d_idx_dense || !d_idx_i32 || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
+  if (row_hi <= row_lo) return GFICF_OK;
+  const int kp = row_stride(k);
+  const long long total = (row_hi - row_lo) * (long long)kp;
+  pad_i32_kernel<<<grid_1d(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      d_idx_dense, n, k, kp, row_lo, row_hi, d_idx_i32, d_flags);
+  CU_TRY(cudaGetLastError());
+  return GFICF_OK;
+  DEV_END
+}
+
+int gficf_cuda_jaccard_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                           int64_t row_hi, double* d_from, double* d_to, double* d_w,
+                           uint32_t* d_flags, void* stream) {
+  DEV_BEGIN
+  if (!d_idx_i32 || !d_from || !d_to || !d_w || !d_flags || k < 1 || row_lo < 0 || row_hi > n)
+    return GFICF_E_ARG;
+  if (!launch_fast<false>(d_idx_i32, k, row_lo, row_hi, d_from, d_to, d_w, nullptr, d_flags,
+                          (cudaStream_t)stream))
+    return GFICF_E_LIMIT;
+  return GFICF_OK;
+  DEV_END
+}
+
+int gficf_cuda_jaccard_counts_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                                  int64_t row_hi, uint8_t* d_u, uint32_t* d_flags, void* stream) {
+  DEV_BEGIN
+  if (!d_idx_i32 || !d_u || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
+  if (!launch_fast<true>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, d_u, d_flags,
+                         (cudaStream_t)stream))
+    return GFICF_E_LIMIT;
+  return GFICF_OK;
+  DEV_END
+}
+
+int gficf_cuda_jaccard_exact_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                                 int64_t row_hi, int32_t set_semantics, void* d_u, void* stream) {
+  DEV_BEGIN
+  if (!d_idx_i32 || !d_u || k < 1 || k > 65535 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
+  launch_exact(d_idx_i32, k, row_lo, row_hi, set_semantics, d_u, (cudaStream_t)stream);
+  return GFICF_OK;
+  DEV_END
+}
+
+size_t gficf_cuda_expand_scratch_bytes(int64_t slab_edges) {
+  return expand_scratch_bytes(slab_edges < 0 ? 0 : slab_edges);
+}
+
+int gficf_cuda_expand_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, int64_t row_hi,
+                          const void* d_u, int32_t mode, double* d_from, double* d_to, double* d_w,
+                          void* d_scratch, int64_t* d_n_written, void* stream) {
+  DEV_BEGIN
+  if (!d_idx_i32 || !d_u || !d_from || !d_to || !d_w || k < 1 || k > 65535 || row_lo < 0)
+    return GFICF_E_ARG;
+  if (mode == GFICF_MODE_SERIAL && (!d_scratch || !d_n_written)) return GFICF_E_ARG;
+  if (mode != GFICF_MODE_SERIAL && mode != GFICF_MODE_PARALLEL) return GFICF_E_ARG;
+  launch_expand(d_idx_i32, k, row_lo, row_hi, d_u, mode, d_from, d_to, d_w, d_scratch,
+                (long long*)d_n_written, (cudaStream_t)stream);
+  return GFICF_OK;
+  DEV_END
+}
+
+}  // extern "C"

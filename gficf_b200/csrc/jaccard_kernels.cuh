@@ -1,0 +1,571 @@
+// jaccard_kernels.cuh -- sm_100a device kernels of the Phenograph Jaccard path.
+//
+// What they replace (reference = dibbelab/gficf):
+//   layout_f64_kernel      the per-edge strided row copies out of the column-major
+//                          double matrix, src/rcpp_parallel_jaccard_coeff.cpp:30-36
+//   jaccard_small_k_kernel JCoefficient::operator() for k<=32,
+//   jaccard_wide_k_kernel  and for 32<k<=128, rcpp_parallel_jaccard_coeff.cpp:24-55
+//   jaccard_exact_kernel   the same for any k and rows with repeated ids
+//                          (std::set_intersection multiset semantics :41-46, or
+//                          Rcpp::intersect unique-set semantics, jaccard_coeff.cpp:33)
+//   expand_* kernels       the conditional (from,to,w) stores :48-52 and the
+//                          compacting stores of jaccard_coeff.cpp:34-39
+//
+// Design (HBM-bound sparse gather; no tensor cores -- there is no dense
+// contraction here):
+//   * the index matrix lives in HBM as int32, row-major, 0-based, rows padded to a
+//     32-byte sector multiple, so a neighbour row is fetched with 16-byte vector
+//     loads (one LDG.128 per lane brings 4 ids; k=30 -> 8 lanes per row, 4 rows
+//     per warp instruction);
+//   * one warp owns row i: N(i) is put into a per-warp COLLISION-FREE
+//     multiplicative hash table in shared memory (a multiplier is searched per
+//     row), so membership of each gathered id is one IMAD+SHF+LDS+compare;
+//   * all gathers of a row are issued before the first probe (up to 8 LDG.128
+//     in flight per lane), the next row's own ids are prefetched;
+//   * per-edge counts are packed 4 per register and reduced across the lanes of
+//     an edge group by xor-shuffles; lane e ends with u(i, e) and writes
+//     from/to/w with coalesced streaming stores (st.global.cs) so that the
+//     output does not evict the index matrix from L2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gficf {
+
+constexpr int kPadId = -2;              // pad entries of an index row (never equals an id or kEmpty)
+constexpr unsigned kEmpty = 0xFFFFFFFFu;  // empty hash slot
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr unsigned kFlagBadId = 1u, kFlagDupId = 2u, kFlagHashFail = 4u;
+constexpr int kMaxTries = 256;
+constexpr unsigned kMult0 = 0x9E3779B1u;  // odd; successive multipliers come from an LCG
+
+__device__ __forceinline__ unsigned next_mult(unsigned m) { return (m * 0x2C1B3C6Du + 0x297A2D39u) | 1u; }
+
+__device__ __forceinline__ int4 ldg16(const int* p) {
+  return __ldg(reinterpret_cast<const int4*>(p));
+}
+
+__device__ __forceinline__ double jaccard_weight(int u, int k) {
+  // rcpp_parallel_jaccard_coeff.cpp:51  u/(2.0*mat.ncol() - u) : exact integer
+  // operands, ONE IEEE-754 double division (correctly rounded on the device too).
+  return __ddiv_rn((double)u, 2.0 * (double)k - (double)u);
+}
+
+// ---------------------------------------------------------------------------
+// Layout pre-pass: f64 column-major 1-based  ->  int32 row-major 0-based, padded.
+// One CTA converts a tile of TILE_R rows: coalesced 256-byte column reads into a
+// shared-memory tile, then the tile (contiguous in the output) leaves with 16-byte
+// stores.
+// ---------------------------------------------------------------------------
+constexpr int kLayoutTileR = 64;
+constexpr int kLayoutThreads = 256;
+
+__global__ void __launch_bounds__(kLayoutThreads)
+layout_f64_kernel(const double* __restrict__ src, long long ld_rows, long long ld_row0, long long n,
+                  int k, int kp, long long row_lo, long long row_hi, int* __restrict__ dst,
+                  unsigned* __restrict__ flags) {
+  extern __shared__ int tile[];  // [kLayoutTileR][kp + 1]
+  const int tid = threadIdx.x;
+  const int stride = kp + 1;
+  const long long ntiles = (row_hi - row_lo + kLayoutTileR - 1) / kLayoutTileR;
+  bool bad = false;
+  for (long long tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+    const long long r0 = row_lo + tb * kLayoutTileR;
+    const int rows = (int)min((long long)kLayoutTileR, row_hi - r0);
+    // column reads: thread -> (row r = tid % 64, column group tid / 64)
+    const int r = tid & (kLayoutTileR - 1);
+    for (int j = tid / kLayoutTileR; j < kp; j += kLayoutThreads / kLayoutTileR) {
+      int v = kPadId;
+      if (j < k && r < rows) {
+        const double d = __ldcs(src + (long long)j * ld_rows + (r0 + r - ld_row0));
+        // ids must be integers in [1,n]; NaN fails the first comparison
+        if (d >= 1.0 && d <= (double)n && d == floor(d)) {
+          v = (int)d - 1;  // :28  int k = mat(i,j)-1
+        } else {
+          bad = true;
+          v = 0;
+        }
+      }
+      tile[r * stride + j] = v;
+    }
+    __syncthreads();
+    // contiguous output: rows*kp ints starting at dst + r0*kp  (kp % 4 == 0, 16B aligned)
+    int4* out4 = reinterpret_cast<int4*>(dst + r0 * (long long)kp);
+    const int nvec = rows * kp / 4;
+    for (int x = tid; x < nvec; x += kLayoutThreads) {
+      const int f = x * 4;
+      const int rr = f / kp, cc = f - rr * kp;
+      const int* t = tile + rr * stride + cc;
+      out4[x] = make_int4(t[0], t[1], t[2], t[3]);
+    }
+    __syncthreads();
+  }
+  if (bad) atomicOr(flags, kFlagBadId);
+}
+
+// int32 dense row-major (k per row, 0-based) -> padded rows.  Validates ids in [0,n).
+__global__ void __launch_bounds__(256)
+pad_i32_kernel(const int* __restrict__ src, long long n, int k, int kp, long long row_lo,
+               long long row_hi, int* __restrict__ dst, unsigned* __restrict__ flags) {
+  const long long total = (row_hi - row_lo) * (long long)kp;
+  bool bad = false;
+  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total;
+       x += (long long)gridDim.x * blockDim.x) {
+    const long long rr = x / kp;
+    const int cc = (int)(x - rr * kp);
+    int v = kPadId;
+    if (cc < k) {
+      v = __ldcs(src + (row_lo + rr) * (long long)k + cc);
+      if (v < 0 || (long long)v >= n) {
+        bad = true;
+        v = 0;
+      }
+    }
+    dst[(row_lo + rr) * (long long)kp + cc] = v;
+  }
+  if (bad) atomicOr(flags, kFlagBadId);
+}
+
+// ---------------------------------------------------------------------------
+// Fast kernel, k <= 32.  KP = padded row length in {4,8,16,32}.
+//   LPE lanes fetch one neighbour row (one int4 each); a warp instruction
+//   therefore gathers EPS = 32/LPE rows; S steps cover the KP edge slots.
+//   Step s, lane group g works on edge e = g*S + s.
+// ---------------------------------------------------------------------------
+template <int KP>
+struct SmallK {
+  static constexpr int LPE = KP / 4;
+  static constexpr int EPS = 32 / LPE;
+  static constexpr int S = (KP >= EPS) ? KP / EPS : 1;
+  // table slots per warp: ~k^2/2 gives a >40% chance that a multiplier is collision free
+  static constexpr int TS = (KP == 32) ? 512 : (KP == 16) ? 128 : 64;
+  static constexpr int LOG_TS = (KP == 32) ? 9 : (KP == 16) ? 7 : 6;
+};
+
+constexpr int kSmallWarps = 8;
+
+template <int KP, bool COUNTS_ONLY>
+__global__ void __launch_bounds__(kSmallWarps * 32, 4)
+jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, long long row_hi,
+                       double* __restrict__ o_from, double* __restrict__ o_to,
+                       double* __restrict__ o_w, uint8_t* __restrict__ o_u,
+                       unsigned* __restrict__ flags) {
+  using G = SmallK<KP>;
+  constexpr int LPE = G::LPE, S = G::S, TS = G::TS, SHIFT = 32 - G::LOG_TS;
+  __shared__ unsigned tbl_all[kSmallWarps][TS];
+  __shared__ double lut[33];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned* tbl = tbl_all[warp];
+#pragma unroll
+  for (int x = lane; x < TS; x += 32) tbl[x] = kEmpty;
+  if ((int)threadIdx.x <= k) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
+  __syncthreads();
+
+  const long long nwarps = (long long)gridDim.x * kSmallWarps;
+  long long row = row_lo + (long long)blockIdx.x * kSmallWarps + warp;
+  const int sub4 = (lane % LPE) * 4;  // which 16-byte piece of a neighbour row this lane fetches
+  const int grp = lane / LPE;
+  const bool valid = lane < k;
+  unsigned warp_flags = 0;
+
+  int a_next = (row < row_hi && lane < KP) ? __ldg(idx + row * KP + lane) : kPadId;
+  for (; row < row_hi; row += nwarps) {
+    const int a = a_next;  // N(i)[lane], 0-based
+    {
+      const long long nrow = row + nwarps;
+      a_next = (nrow < row_hi && lane < KP) ? __ldg(idx + nrow * KP + lane) : kPadId;
+    }
+    // ---- gather addresses first: the loads do not depend on the hash table
+    int4 v[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int e = grp * S + s;
+      const int t = __shfl_sync(kFull, a, e & 31);
+      v[s] = (e < k) ? ldg16(idx + (long long)t * KP + sub4)
+                     : make_int4(kPadId, kPadId, kPadId, kPadId);
+    }
+    // ---- collision-free hash of N(i): search a multiplier
+    unsigned mult = kMult0, slot;
+    bool dup = false;
+    int tries = 0;
+    for (;;) {
+      slot = ((unsigned)a * mult) >> SHIFT;
+      if (valid) tbl[slot] = (unsigned)lane;
+      __syncwarp();
+      const int owner = valid ? (int)tbl[slot] : lane;
+      const int okey = __shfl_sync(kFull, a, owner);
+      const bool lost = owner != lane;
+      const bool coll = lost && okey != a;
+      dup |= lost && okey == a;
+      if (!__any_sync(kFull, coll)) break;
+      if (++tries == kMaxTries) {
+        warp_flags |= kFlagHashFail;
+        break;
+      }
+      if (valid) tbl[slot] = kEmpty;
+      __syncwarp();
+      mult = next_mult(mult);
+    }
+    if (valid) tbl[slot] = (unsigned)a;
+    if (__any_sync(kFull, dup)) warp_flags |= kFlagDupId;
+    __syncwarp();
+    // ---- probe the gathered ids; counts of up to 4 steps packed per register
+    unsigned c_lo = 0, c_hi = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const unsigned x0 = (unsigned)v[s].x, x1 = (unsigned)v[s].y, x2 = (unsigned)v[s].z,
+                     x3 = (unsigned)v[s].w;
+      unsigned h = 0;
+      h += tbl[(x0 * mult) >> SHIFT] == x0;
+      h += tbl[(x1 * mult) >> SHIFT] == x1;
+      h += tbl[(x2 * mult) >> SHIFT] == x2;
+      h += tbl[(x3 * mult) >> SHIFT] == x3;
+      if (s < 4) c_lo += h << (8 * (s & 3));
+      else c_hi += h << (8 * (s & 3));
+    }
+#pragma unroll
+    for (int m = 1; m < LPE; m <<= 1) {
+      c_lo += __shfl_xor_sync(kFull, c_lo, m);
+      if (S > 4) c_hi += __shfl_xor_sync(kFull, c_hi, m);
+    }
+    // lane e wants edge e = g*S+s  ->  group e/S, byte e%S
+    unsigned p_lo = c_lo, p_hi = c_hi;
+    if (S != LPE) {
+      const int src = ((lane / S) * LPE) & 31;
+      p_lo = __shfl_sync(kFull, c_lo, src);
+      if (S > 4) p_hi = __shfl_sync(kFull, c_hi, src);
+    }
+    const int sb = lane % S;
+    const unsigned word = (S > 4 && sb >= 4) ? p_hi : p_lo;
+    const int u = (int)((word >> (8 * (sb & 3))) & 0xFFu);
+    __syncwarp();
+    if (valid) tbl[slot] = kEmpty;  // leave the table empty for the next row
+    // ---- epilogue: lane e writes edge (i, e)
+    if (valid) {
+      const long long r = (row - row_lo) * (long long)k + lane;
+      if (COUNTS_ONLY) {
+        o_u[r] = (uint8_t)u;
+      } else {
+        const bool nz = u > 0;  // :48 if(u>0), else the zero-filled row stays
+        __stcs(o_from + r, nz ? (double)(row + 1) : 0.0);
+        __stcs(o_to + r, nz ? (double)(a + 1) : 0.0);
+        __stcs(o_w + r, lut[u]);
+      }
+    }
+    __syncwarp();
+  }
+  if (warp_flags && lane == 0) atomicOr(flags, warp_flags);
+}
+
+// ---------------------------------------------------------------------------
+// Fast kernel, 32 < k <= 128: the whole warp fetches ONE neighbour row per load
+// instruction (lane l brings ids 4l..4l+3), U rows in flight per batch.
+// ---------------------------------------------------------------------------
+constexpr int kWideWarps = 4;
+constexpr int kWideU = 8;  // neighbour rows in flight per warp
+
+template <int LOG_TS, bool COUNTS_ONLY>
+__global__ void __launch_bounds__(kWideWarps * 32)
+jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo,
+                      long long row_hi, double* __restrict__ o_from, double* __restrict__ o_to,
+                      double* __restrict__ o_w, uint8_t* __restrict__ o_u,
+                      unsigned* __restrict__ flags) {
+  constexpr int TS = 1 << LOG_TS, SHIFT = 32 - LOG_TS;
+  extern __shared__ unsigned smem_u[];
+  // per warp: table[TS] | own row ids[128] | counts[128]
+  constexpr int PER_WARP = TS + 128 + 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned* tbl = smem_u + warp * PER_WARP;
+  int* srow = reinterpret_cast<int*>(tbl + TS);
+  int* scnt = srow + 128;
+  double* lut = reinterpret_cast<double*>(smem_u + kWideWarps * PER_WARP);  // [129]
+
+  for (int x = lane; x < TS; x += 32) tbl[x] = kEmpty;
+  for (int x = threadIdx.x; x <= k; x += blockDim.x) lut[x] = jaccard_weight(x, k);
+  __syncthreads();
+
+  const long long nwarps = (long long)gridDim.x * kWideWarps;
+  const int c0 = lane * 4;
+  const bool lane_on = c0 < kp;
+  const int4 pad4 = make_int4(kPadId, kPadId, kPadId, kPadId);
+  unsigned warp_flags = 0;
+
+  for (long long row = row_lo + (long long)blockIdx.x * kWideWarps + warp; row < row_hi;
+       row += nwarps) {
+    const int4 a4 = lane_on ? ldg16(idx + row * (long long)kp + c0) : pad4;
+    const int av[4] = {a4.x, a4.y, a4.z, a4.w};
+    *reinterpret_cast<int4*>(srow + c0) = a4;
+    __syncwarp();
+    // ---- collision-free hash of N(i)
+    unsigned mult = kMult0;
+    unsigned slot[4];
+    bool dup = false;
+    int tries = 0;
+    for (;;) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        slot[c] = ((unsigned)av[c] * mult) >> SHIFT;
+        if (c0 + c < k) tbl[slot[c]] = (unsigned)(c0 + c);
+      }
+      __syncwarp();  // whichever writer survives in a slot, every other one sees it lost
+      bool coll = false;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c0 + c < k) {
+          const int owner = (int)tbl[slot[c]];
+          const int okey = srow[owner];
+          const bool lost = owner != c0 + c;
+          coll |= lost && okey != av[c];
+          dup |= lost && okey == av[c];
+        }
+      }
+      if (!__any_sync(kFull, coll)) break;
+      if (++tries == kMaxTries) {
+        warp_flags |= kFlagHashFail;
+        break;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c0 + c < k) tbl[slot[c]] = kEmpty;
+      __syncwarp();
+      mult = next_mult(mult);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c0 + c < k) tbl[slot[c]] = (unsigned)av[c];
+    if (__any_sync(kFull, dup)) warp_flags |= kFlagDupId;
+    __syncwarp();
+
+    // ---- batches of U neighbour rows
+    for (int e0 = 0; e0 < k; e0 += kWideU) {
+      int4 v[kWideU];
+#pragma unroll
+      for (int q = 0; q < kWideU; ++q) {
+        const int e = e0 + q;
+        v[q] = pad4;
+        if (e < k && lane_on) {
+          const int t = srow[e];
+          v[q] = ldg16(idx + (long long)t * kp + c0);
+        }
+      }
+      unsigned acc[kWideU / 4];
+#pragma unroll
+      for (int q = 0; q < kWideU / 4; ++q) acc[q] = 0;
+#pragma unroll
+      for (int q = 0; q < kWideU; ++q) {
+        const unsigned x0 = (unsigned)v[q].x, x1 = (unsigned)v[q].y, x2 = (unsigned)v[q].z,
+                       x3 = (unsigned)v[q].w;
+        unsigned h = 0;
+        h += tbl[(x0 * mult) >> SHIFT] == x0;
+        h += tbl[(x1 * mult) >> SHIFT] == x1;
+        h += tbl[(x2 * mult) >> SHIFT] == x2;
+        h += tbl[(x3 * mult) >> SHIFT] == x3;
+        acc[q >> 2] += h << (8 * (q & 3));  // per byte: <= 4*32 = 128 after the reduction
+      }
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) {
+#pragma unroll
+        for (int q = 0; q < kWideU / 4; ++q) acc[q] += __shfl_xor_sync(kFull, acc[q], m);
+      }
+      if (lane < kWideU && e0 + lane < k) {
+        unsigned word = acc[0];
+#pragma unroll
+        for (int q = 1; q < kWideU / 4; ++q)
+          if ((lane >> 2) == q) word = acc[q];
+        scnt[e0 + lane] = (int)((word >> (8 * (lane & 3))) & 0xFFu);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c0 + c < k) tbl[slot[c]] = kEmpty;
+    // ---- epilogue: coalesced, lane -> edges lane, lane+32, ...
+    for (int e = lane; e < k; e += 32) {
+      const int u = scnt[e];
+      const long long r = (row - row_lo) * (long long)k + e;
+      if (COUNTS_ONLY) {
+        o_u[r] = (uint8_t)u;
+      } else {
+        const bool nz = u > 0;
+        __stcs(o_from + r, nz ? (double)(row + 1) : 0.0);
+        __stcs(o_to + r, nz ? (double)(srow[e] + 1) : 0.0);
+        __stcs(o_w + r, lut[u]);
+      }
+    }
+    __syncwarp();
+  }
+  if (warp_flags && lane == 0) atomicOr(flags, warp_flags);
+}
+
+// ---------------------------------------------------------------------------
+// Exact kernel: any k, rows may repeat ids.  One thread per edge, O(k^2).
+//   multiset:  u = sum_p [ rank_t(p) < cnt_i(t_p) ]   = sum_v min(cnt_i(v), cnt_t(v))
+//   set:       u = sum_p [ rank_t(p)==0 && cnt_i(t_p)>0 ]
+// where rank_t(p) = #{q<p : t_q == t_p}.
+// ---------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(128)
+jaccard_exact_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo, long long row_hi,
+                     int set_semantics, CT* __restrict__ o_u) {
+  const long long total = (row_hi - row_lo) * (long long)k;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total;
+       r += (long long)gridDim.x * blockDim.x) {
+    const long long i = row_lo + r / k;
+    const int j = (int)(r % k);
+    const int* ri = idx + i * (long long)kp;
+    const int* rt = idx + (long long)ri[j] * kp;
+    int u = 0;
+    for (int p = 0; p < k; ++p) {
+      const int x = rt[p];
+      int rank = 0;
+      for (int q = 0; q < p; ++q) rank += rt[q] == x;
+      int cnt = 0;
+      for (int q = 0; q < k; ++q) cnt += ri[q] == x;
+      u += set_semantics ? (rank == 0 && cnt > 0) : (rank < cnt);
+    }
+    o_u[r] = (CT)u;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// counts -> edge rows, fixed slots (mode 0).  One thread per edge, streaming.
+// ---------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(256)
+expand_fixed_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo, long long row_hi,
+                    const CT* __restrict__ d_u, double* __restrict__ o_from,
+                    double* __restrict__ o_to, double* __restrict__ o_w) {
+  const long long total = (row_hi - row_lo) * (long long)k;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total;
+       r += (long long)gridDim.x * blockDim.x) {
+    const long long rr = r / k;
+    const int j = (int)(r - rr * k);
+    const int u = (int)d_u[r];
+    const bool nz = u > 0;
+    const int t = nz ? __ldg(idx + (row_lo + rr) * (long long)kp + j) : 0;
+    __stcs(o_from + r, nz ? (double)(row_lo + rr + 1) : 0.0);
+    __stcs(o_to + r, nz ? (double)(t + 1) : 0.0);
+    __stcs(o_w + r, nz ? jaccard_weight(u, k) : 0.0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// counts -> edge rows, compacted (mode 1): rows with u>0 in (i,j) order, the
+// tail zero-filled.  Three passes: per-chunk counts, scan of the chunk counts,
+// scatter.
+// ---------------------------------------------------------------------------
+constexpr int kCompactChunk = 4096;  // edges per CTA
+constexpr int kCompactThreads = 256;
+
+template <typename CT>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_count_kernel(const CT* __restrict__ d_u, long long total, long long* __restrict__ chunk_cnt) {
+  __shared__ int wsum[kCompactThreads / 32];
+  const long long base = (long long)blockIdx.x * kCompactChunk;
+  int c = 0;
+  for (int x = threadIdx.x; x < kCompactChunk; x += kCompactThreads) {
+    const long long r = base + x;
+    c += (r < total) && d_u[r] != 0;
+  }
+  for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(kFull, c, m);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < kCompactThreads / 32; ++w) s += wsum[w];
+    chunk_cnt[blockIdx.x] = s;
+  }
+}
+
+// exclusive scan of chunk counts in place, single CTA; total -> *n_written
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(long long* __restrict__ chunk_cnt, long long nchunks,
+                    long long* __restrict__ n_written) {
+  __shared__ long long wtot[32];
+  __shared__ long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long b = 0; b < nchunks; b += 1024) {
+    const long long x = b + threadIdx.x;
+    const long long v = x < nchunks ? chunk_cnt[x] : 0;
+    long long inc = v;
+    for (int m = 1; m < 32; m <<= 1) {
+      const long long o = __shfl_up_sync(kFull, inc, m);
+      if (lane >= m) inc += o;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = wtot[lane];
+      for (int m = 1; m < 32; m <<= 1) {
+        const long long o = __shfl_up_sync(kFull, w, m);
+        if (lane >= m) w += o;
+      }
+      wtot[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const long long carry = carry_s;
+    const long long before = carry + (warp ? wtot[warp - 1] : 0) + inc - v;
+    if (x < nchunks) chunk_cnt[x] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wtot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_written = carry_s;
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_scatter_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo,
+                       const CT* __restrict__ d_u, long long total,
+                       const long long* __restrict__ chunk_off, double* __restrict__ o_from,
+                       double* __restrict__ o_to, double* __restrict__ o_w) {
+  __shared__ int wsum[kCompactThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long base = (long long)blockIdx.x * kCompactChunk;
+  long long off = chunk_off[blockIdx.x];
+  for (int x0 = 0; x0 < kCompactChunk; x0 += kCompactThreads) {
+    const long long r = base + x0 + threadIdx.x;
+    const int u = (r < total) ? (int)d_u[r] : 0;
+    const bool nz = u > 0;
+    const unsigned b = __ballot_sync(kFull, nz);
+    if (lane == 0) wsum[warp] = __popc(b);
+    __syncthreads();
+    int before = __popc(b & ((1u << lane) - 1u));
+    int all = 0;
+    for (int w = 0; w < kCompactThreads / 32; ++w) {
+      const int s = wsum[w];
+      if (w < warp) before += s;
+      all += s;
+    }
+    if (nz) {
+      const long long rr = r / k;
+      const int j = (int)(r - rr * k);
+      const int t = __ldg(idx + (row_lo + rr) * (long long)kp + j);
+      const long long o = off + before;
+      __stcs(o_from + o, (double)(row_lo + rr + 1));
+      __stcs(o_to + o, (double)(t + 1));
+      __stcs(o_w + o, jaccard_weight(u, k));
+    }
+    off += all;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zero_tail_kernel(const long long* __restrict__ n_written, long long total, double* __restrict__ o_from,
+                 double* __restrict__ o_to, double* __restrict__ o_w) {
+  const long long start = *n_written;
+  for (long long r = start + (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total;
+       r += (long long)gridDim.x * blockDim.x) {
+    o_from[r] = 0.0;
+    o_to[r] = 0.0;
+    o_w[r] = 0.0;
+  }
+}
+
+}  // namespace gficf

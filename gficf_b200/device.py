@@ -1,0 +1,138 @@
+"""Device-resident entry points on torch CUDA tensors (torch is only the allocator / stream
+provider here; every kernel is the library's own, called through the C ABI of
+include/gficf_cuda.h).
+
+Index layout on the device: int32, row-major, 0-based, ``row_stride(k)`` ints per row, pad = -2.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+FLAG_BAD_ID, FLAG_DUP_ID, FLAG_HASH_FAIL = 1, 2, 4
+
+
+def row_stride(k: int) -> int:
+    return int(_lib.lib().gficf_cuda_row_stride(int(k)))
+
+
+def _stream_ptr() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, dtype) -> None:
+    if not t.is_cuda:
+        raise ValueError("a CUDA tensor is required (this package has no CPU implementation)")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise ValueError("expected a contiguous %s tensor" % dtype)
+
+
+def new_flags(device) -> torch.Tensor:
+    return torch.zeros(2, dtype=torch.int32, device=device)
+
+
+def layout_from_r_matrix(d_idx_f64_colmajor: torch.Tensor, n: int, k: int, out: torch.Tensor | None = None,
+                         flags: torch.Tensor | None = None, row_lo: int = 0, row_hi: int | None = None):
+    """f64 column-major 1-based (a device copy of the R matrix, passed as a 1-D or (k, n)
+    contiguous tensor) -> padded int32 rows.  Returns (idx_i32 [n, stride], flags)."""
+    _require_cuda(d_idx_f64_colmajor, torch.float64)
+    stride = row_stride(k)
+    dev = d_idx_f64_colmajor.device
+    if out is None:
+        out = torch.empty((n, stride), dtype=torch.int32, device=dev)
+    if flags is None:
+        flags = new_flags(dev)
+    hi = n if row_hi is None else row_hi
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().gficf_cuda_layout_dev(d_idx_f64_colmajor.data_ptr(), n, 0, n, k, row_lo, hi,
+                                                    out.data_ptr(), flags.data_ptr(), _stream_ptr()))
+    return out, flags
+
+
+def pad_rows(d_idx_dense_i32: torch.Tensor, out: torch.Tensor | None = None,
+             flags: torch.Tensor | None = None):
+    """int32 [n, k] row-major 0-based (e.g. from a GPU kNN) -> padded int32 rows."""
+    _require_cuda(d_idx_dense_i32, torch.int32)
+    n, k = d_idx_dense_i32.shape
+    stride = row_stride(k)
+    dev = d_idx_dense_i32.device
+    if out is None:
+        out = torch.empty((n, stride), dtype=torch.int32, device=dev)
+    if flags is None:
+        flags = new_flags(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().gficf_cuda_pad_dev(d_idx_dense_i32.data_ptr(), n, k, 0, n, out.data_ptr(),
+                                                 flags.data_ptr(), _stream_ptr()))
+    return out, flags
+
+
+def jaccard_edges(idx_i32: torch.Tensor, n: int, k: int, row_lo: int = 0, row_hi: int | None = None,
+                  out: torch.Tensor | None = None, flags: torch.Tensor | None = None):
+    """Fused fast kernel: rows [row_lo,row_hi) -> out[3, slab_edges] float64 (from, to, w)."""
+    _require_cuda(idx_i32, torch.int32)
+    hi = n if row_hi is None else row_hi
+    e = (hi - row_lo) * k
+    dev = idx_i32.device
+    if out is None:
+        out = torch.empty((3, e), dtype=torch.float64, device=dev)
+    if flags is None:
+        flags = new_flags(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().gficf_cuda_jaccard_dev(idx_i32.data_ptr(), n, k, row_lo, hi, out[0].data_ptr(),
+                                                     out[1].data_ptr(), out[2].data_ptr(), flags.data_ptr(),
+                                                     _stream_ptr()))
+    return out, flags
+
+
+def jaccard_counts(idx_i32: torch.Tensor, n: int, k: int, row_lo: int = 0, row_hi: int | None = None,
+                   out: torch.Tensor | None = None, flags: torch.Tensor | None = None):
+    """Fast kernel, intersection counts only: uint8 [slab_edges] (k <= 128)."""
+    _require_cuda(idx_i32, torch.int32)
+    hi = n if row_hi is None else row_hi
+    e = (hi - row_lo) * k
+    dev = idx_i32.device
+    if out is None:
+        out = torch.empty((e,), dtype=torch.uint8, device=dev)
+    if flags is None:
+        flags = new_flags(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().gficf_cuda_jaccard_counts_dev(idx_i32.data_ptr(), n, k, row_lo, hi,
+                                                            out.data_ptr(), flags.data_ptr(), _stream_ptr()))
+    return out, flags
+
+
+def jaccard_counts_exact(idx_i32: torch.Tensor, n: int, k: int, set_semantics: bool, row_lo: int = 0,
+                         row_hi: int | None = None):
+    """Exact kernel (rows may repeat ids, any k): uint8 counts (k<=255) or int16-typed uint16."""
+    _require_cuda(idx_i32, torch.int32)
+    hi = n if row_hi is None else row_hi
+    e = (hi - row_lo) * k
+    dev = idx_i32.device
+    out = torch.empty((e,), dtype=torch.uint8 if k <= 255 else torch.int16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().gficf_cuda_jaccard_exact_dev(idx_i32.data_ptr(), n, k, row_lo, hi,
+                                                           int(bool(set_semantics)), out.data_ptr(),
+                                                           _stream_ptr()))
+    return out
+
+
+def expand(idx_i32: torch.Tensor, k: int, counts: torch.Tensor, mode: int = 0, row_lo: int = 0,
+           row_hi: int | None = None, out: torch.Tensor | None = None):
+    """counts -> (from, to, w) rows.  mode 0 fixed slots; mode 1 compacted (returns n_written too)."""
+    _require_cuda(idx_i32, torch.int32)
+    hi = idx_i32.shape[0] if row_hi is None else row_hi
+    e = (hi - row_lo) * k
+    dev = idx_i32.device
+    if out is None:
+        out = torch.empty((3, e), dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    scratch = torch.empty((max(int(L.gficf_cuda_expand_scratch_bytes(e)), 8),), dtype=torch.uint8, device=dev)
+    nw = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.gficf_cuda_expand_dev(idx_i32.data_ptr(), k, row_lo, hi, counts.data_ptr(), mode,
+                                           out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                           scratch.data_ptr(), nw.data_ptr(), _stream_ptr()))
+    return out, nw

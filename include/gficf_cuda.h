@@ -1,0 +1,187 @@
+/* gficf_cuda.h -- C ABI of the B200-native Phenograph Jaccard edge-weighting path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no R / Rcpp / torch
+ * types.  The library behind it (gficf_b200/libgficf_cuda.so, built by nvcc for
+ * sm_100a) replaces the bodies of the two native functions that gficf's Rcpp
+ * shims call:
+ *
+ *   rcpp_parallel_jaccard_coef(NumericMatrix mat, bool printOutput)
+ *       reference: src/rcpp_parallel_jaccard_coeff.cpp:58-80 (worker :24-55),
+ *       bound from R through src/RcppExports.cpp:61-70
+ *   jaccard_coeff(NumericMatrix idx, bool printOutput)
+ *       reference: src/jaccard_coeff.cpp:19-45,
+ *       bound from R through src/RcppExports.cpp:36-45
+ *
+ * Conventions (all the reference's):
+ *   idx  n x k doubles, COLUMN-major (element (i,j) at idx[j*n+i]), values are
+ *        1-based neighbour ids (R coerces uwot's integer matrix to REALSXP at
+ *        src/RcppExports.cpp:40,65)
+ *   out  (n*k) x 3 doubles, COLUMN-major, i.e. three contiguous arrays of
+ *        E = n*k doubles: from[], to[], weight[]
+ *        (rcpp_parallel_jaccard_coeff.cpp:67, jaccard_coeff.cpp:21)
+ *
+ * Every function returns 0 on success and a GFICF_E_* code otherwise; when an
+ * `err` buffer is supplied a NUL-terminated message is written to it.  Nothing
+ * here calls the R API, longjmps or throws across the boundary.  There is no
+ * CPU fallback: without a usable CUDA device the calls fail with
+ * GFICF_E_CUDA.
+ */
+#ifndef GFICF_CUDA_H
+#define GFICF_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes ------------------------------------------------------- */
+#define GFICF_OK 0
+#define GFICF_E_ARG 1    /* bad argument (null pointer, negative size, unknown mode ...)   */
+#define GFICF_E_RANGE 2  /* a neighbour id is NaN, non-integer or outside [1,n]: the        */
+                         /* reference indexes out of bounds there (UB at                    */
+                         /* rcpp_parallel_jaccard_coeff.cpp:28 / jaccard_coeff.cpp:30)      */
+#define GFICF_E_CUDA 3   /* CUDA runtime / driver error, or no device                       */
+#define GFICF_E_NCCL 4   /* NCCL could not be loaded or a collective failed                 */
+#define GFICF_E_LIMIT 5  /* size beyond what the path supports (n*k or n >= 2^31, as in the */
+                         /* reference, whose row index is an `int`)                         */
+
+/* ---- output modes ------------------------------------------------------- */
+/* Fixed slots, multiset intersection: output row r = i*k+j, rows with an empty
+ * intersection stay (0,0,0).  = rcpp_parallel_jaccard_coef
+ * (rcpp_parallel_jaccard_coeff.cpp:41-52). */
+#define GFICF_MODE_PARALLEL 0
+/* Compacted rows, unique-set intersection: a row is emitted (r++) only when
+ * u>0, trailing rows stay zero.  = jaccard_coeff (jaccard_coeff.cpp:33-39). */
+#define GFICF_MODE_SERIAL 1
+
+/* ---- flag bits reported by the device kernels (d_flags) ------------------ */
+#define GFICF_FLAG_BAD_ID 1u     /* layout pre-pass met an id that is NaN / non-integer / out of [1,n] */
+#define GFICF_FLAG_DUP_ID 2u     /* some row lists the same id twice: the exact kernels must be used  */
+#define GFICF_FLAG_HASH_FAIL 4u  /* a row found no collision-free hash: the exact kernels must be used */
+
+/* ======================================================================== *
+ *  Host-buffer entry points (what the Rcpp functions call)
+ * ======================================================================== */
+
+/* The whole path on host buffers: H2D of idx, layout pre-pass, Jaccard
+ * kernel(s), D2H of the three output columns.  `out` is fully written
+ * (the caller need not zero it).  n_devices >= 1 shards cell rows over that
+ * many GPUs of this node (NCCL all-gather of the int32 index slabs, each GPU
+ * returns its own edge slab); n_devices == 0 uses the value set by
+ * gficf_cuda_set_devices() (default 1).
+ *
+ * Replaces: rcpp_parallel_jaccard_coef body (mode 0) and jaccard_coeff body
+ * (mode 1; always one device, its rows are compacted across the whole matrix).
+ * If n_written is non-NULL it receives the number of emitted rows in mode 1
+ * (the reference's final r) and -1 in mode 0. */
+int gficf_cuda_jaccard(const double* idx_colmajor, int64_t n, int32_t k, double* out_colmajor,
+                       int32_t n_devices, int32_t mode, int64_t* n_written, char* err,
+                       size_t errlen);
+
+/* Device-count option that R/clustCells.R's new `n.gpu` argument sets without
+ * changing the arity of the registered .Call routines
+ * (src/RcppExports.cpp:85-92).  Also read once from the environment variable
+ * GFICF_CUDA_DEVICES. */
+int gficf_cuda_set_devices(int32_t n_devices);
+int gficf_cuda_get_devices(void);
+/* Number of visible CUDA devices (0 if none / no driver). */
+int gficf_cuda_device_count(void);
+
+/* Page-locked host buffers so that the H2D / D2H legs run at PCIe speed
+ * without a staging copy (ordinary pageable memory is accepted everywhere,
+ * it is staged through internal pinned buffers). */
+int gficf_cuda_host_alloc(void** p, size_t bytes);
+int gficf_cuda_host_free(void* p);
+
+/* Drop the cached device / pinned workspaces and NCCL communicators. */
+int gficf_cuda_release(void);
+
+/* Timings (milliseconds, CUDA events) of the last gficf_cuda_jaccard call on
+ * this thread: [0] H2D, [1] layout pre-pass, [2] Jaccard kernel(s),
+ * [3] D2H (overlapped portion included), [4] whole call wall-clock,
+ * [5] index all-gather (n_devices>1), [6] kernels launched, [7] reserved. */
+int gficf_cuda_last_timings(double* ms8);
+
+/* ======================================================================== *
+ *  Device-buffer entry points (resident data: the benchmarked kernels, and
+ *  the building blocks a multi-process (one rank per GPU) caller shards with)
+ *  All pointers are device pointers on the CURRENT device; `stream` is a
+ *  cudaStream_t passed as void* (NULL = default stream).  Asynchronous.
+ * ======================================================================== */
+
+/* Row stride (in int32 elements) of the device index layout for a given k:
+ * rows are padded so that every row starts on a 32-byte sector and is read
+ * with 16-byte vector loads (k<=4:4, <=8:8, <=16:16, <=32:32, else k rounded
+ * up to a multiple of 8).  Pad entries hold -2. */
+int32_t gficf_cuda_row_stride(int32_t k);
+
+/* Layout pre-pass for rows [row_lo,row_hi): n x k f64 column-major 1-based
+ * (device copy of the R matrix, leading dimension ld_rows >= row count held;
+ * element (i,j) of the FULL matrix is at d_idx_f64[j*ld_rows + (i-ld_row0)])
+ * -> int32 row-major 0-based with gficf_cuda_row_stride(k) ints per row,
+ * written at d_idx_i32[i*stride ...].  Validates ids (sets GFICF_FLAG_BAD_ID
+ * in *d_flags).
+ * Replaces the per-edge strided row copies of
+ * rcpp_parallel_jaccard_coeff.cpp:30-36. */
+int gficf_cuda_layout_dev(const double* d_idx_f64, int64_t ld_rows, int64_t ld_row0, int64_t n,
+                          int32_t k, int64_t row_lo, int64_t row_hi, int32_t* d_idx_i32,
+                          uint32_t* d_flags, void* stream);
+
+/* Same, from an int32 n x k ROW-major 0-based matrix with k ints per row
+ * (what a GPU kNN would hand over): pads rows, validates ids in [0,n). */
+int gficf_cuda_pad_dev(const int32_t* d_idx_dense, int64_t n, int32_t k, int64_t row_lo,
+                       int64_t row_hi, int32_t* d_idx_i32, uint32_t* d_flags, void* stream);
+
+/* Jaccard edges of rows [row_lo,row_hi), gathering from the full padded index
+ * (all n rows must be resident).  Fixed-slot output (mode 0 semantics):
+ * d_from/d_to/d_w point at the slab's first element, i.e. edge (i,j) is
+ * written at [(i-row_lo)*k + j].  Sets GFICF_FLAG_DUP_ID / GFICF_FLAG_HASH_FAIL
+ * in *d_flags when the fast kernel's result must not be used (then call
+ * gficf_cuda_jaccard_exact_dev).
+ * Replaces JCoefficient::operator() (rcpp_parallel_jaccard_coeff.cpp:24-55). */
+int gficf_cuda_jaccard_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                           int64_t row_hi, double* d_from, double* d_to, double* d_w,
+                           uint32_t* d_flags, void* stream);
+
+/* Same rows, but only the intersection counts u (one byte per edge when
+ * k<=255, layout [(i-row_lo)*k+j]); the compact form that crosses NVLink /
+ * feeds gficf_cuda_expand_dev. */
+int gficf_cuda_jaccard_counts_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                                  int64_t row_hi, uint8_t* d_u, uint32_t* d_flags, void* stream);
+
+/* Exact (any input: duplicate ids inside a row allowed; any k <= 65535) counts
+ * for rows [row_lo,row_hi): set_semantics==0 -> multiset min-count intersection
+ * (std::set_intersection, rcpp_parallel_jaccard_coeff.cpp:41-46);
+ * set_semantics==1 -> number of distinct common ids (Rcpp::intersect,
+ * jaccard_coeff.cpp:33).  d_u holds uint8 per edge when k<=255, else uint16.
+ * Slow path, O(k^2) per edge. */
+int gficf_cuda_jaccard_exact_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                                 int64_t row_hi, int32_t set_semantics, void* d_u, void* stream);
+
+/* Counts -> edge rows for rows [row_lo,row_hi) (d_u: uint8 per edge when
+ * k<=255, else uint16; d_from/d_to/d_w point at the slab's first element).
+ * mode 0: fixed slots, edge (i,j) at [(i-row_lo)*k+j], zeros where u==0.
+ * mode 1: rows with u>0 compacted in (i,j) order from element 0 on, the tail
+ *         up to the slab's (row_hi-row_lo)*k rows zero-filled; d_scratch must
+ *         hold gficf_cuda_expand_scratch_bytes(slab edges) bytes and the
+ *         emitted-row count is stored to *d_n_written (int64, device memory).
+ * Replaces the conditional stores rcpp_parallel_jaccard_coeff.cpp:48-52 /
+ * jaccard_coeff.cpp:34-39. */
+int gficf_cuda_expand_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, int64_t row_hi,
+                          const void* d_u, int32_t mode, double* d_from, double* d_to, double* d_w,
+                          void* d_scratch, int64_t* d_n_written, void* stream);
+size_t gficf_cuda_expand_scratch_bytes(int64_t slab_edges);
+
+/* Launch geometry of the last fast-kernel launch on this thread (for the
+ * bench record): grid, block, dynamic smem bytes, kernels launched. */
+int gficf_cuda_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* variant);
+
+/* Library / build identification, e.g. "gficf_cuda 0.1 sm_100a". */
+const char* gficf_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFICF_CUDA_H */

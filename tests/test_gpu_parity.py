@@ -1,0 +1,197 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (gficf_b200 -> libgficf_cuda.so),
+against the oracle on the same inputs -- bit-exact (np.array_equal on the float64 matrices:
+identical intersection counts, identical IEEE doubles, same row order)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gficf_b200 import synth
+from tests.conftest import random_knn
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_vectors(cuda, path):
+    """Outputs of the reference itself (tests/golden/make_golden.py)."""
+    g = np.load(path)
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(g["idx"]), g["parallel"])
+    assert np.array_equal(cuda.jaccard_coeff(g["idx"]), g["serial"])
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 29, 30, 31, 32])
+def test_small_k_kernel_all_widths(cuda, oracle, k):
+    rng = np.random.default_rng(k)
+    idx = random_knn(rng, 1537, k)
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(idx), oracle.parallel(idx))
+    assert np.array_equal(cuda.jaccard_coeff(idx), oracle.serial(idx))
+
+
+@pytest.mark.parametrize("k", [33, 40, 48, 49, 63, 64, 65, 99, 100, 127, 128])
+def test_wide_k_kernel(cuda, oracle, k):
+    rng = np.random.default_rng(k)
+    idx = random_knn(rng, 700, k)
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(idx), oracle.parallel(idx))
+
+
+@pytest.mark.parametrize("k", [129, 200, 300])
+def test_exact_kernel_large_k(cuda, oracle, k):
+    rng = np.random.default_rng(k)
+    idx = random_knn(rng, 400, k)
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(idx), oracle.parallel(idx))
+    assert np.array_equal(cuda.jaccard_coeff(idx), oracle.serial(idx))
+
+
+@pytest.mark.parametrize("n,k", [(500, 8), (300, 30), (200, 64), (150, 100)])
+def test_repeated_ids_take_the_exact_path(cuda, oracle, n, k):
+    """Rows that list an id twice: multiset semantics in the parallel export
+    (std::set_intersection), unique-set semantics in the serial one (Rcpp::intersect)."""
+    rng = np.random.default_rng(n + k)
+    idx = random_knn(rng, n, k, distinct=False)
+    par, ser = oracle.parallel(idx), oracle.serial(idx)
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(idx), par)
+    assert np.array_equal(cuda.jaccard_coeff(idx), ser)
+    # one single repeated id in an otherwise clean matrix must be noticed too
+    idx2 = random_knn(rng, n, k)
+    idx2[n // 2, 0] = idx2[n // 2, k - 1]
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(idx2), oracle.parallel(idx2))
+    assert np.array_equal(cuda.jaccard_coeff(idx2), oracle.serial(idx2))
+
+
+def test_self_in_own_list_and_identical_lists(cuda, oracle):
+    rng = np.random.default_rng(1)
+    idx = random_knn(rng, 400, 30, with_self=True)
+    idx[:, 0] = np.arange(1, 401)  # t == i  ->  u == k  ->  w == 1.0
+    out = cuda.rcpp_parallel_jaccard_coef(idx)
+    assert np.array_equal(out, oracle.parallel(idx))
+    assert (out[0::30, 2] == 1.0).all()
+
+
+def test_integer_matrix_is_coerced_like_rcpp(cuda, oracle):
+    rng = np.random.default_rng(2)
+    idx = random_knn(rng, 300, 15)
+    as_int = np.ascontiguousarray(idx.astype(np.int32))  # C order, integer: what uwot returns
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(as_int), oracle.parallel(idx))
+
+
+def test_invalid_ids_are_rejected(cuda):
+    rng = np.random.default_rng(3)
+    base = random_knn(rng, 200, 15)
+    for bad in (0.0, 201.0, -3.0, 2.5, np.nan, np.inf):
+        idx = base.copy()
+        idx[17, 4] = bad
+        with pytest.raises(cuda.GficfCudaError) as e:
+            cuda.rcpp_parallel_jaccard_coef(idx)
+        assert e.value.code == 2  # GFICF_E_RANGE
+    # and the library is still usable afterwards
+    assert cuda.rcpp_parallel_jaccard_coef(base).shape == (3000, 3)
+
+
+def test_empty_and_tiny(cuda, oracle):
+    assert cuda.rcpp_parallel_jaccard_coef(np.empty((0, 5))).shape == (0, 3)
+    assert cuda.rcpp_parallel_jaccard_coef(np.empty((5, 0))).shape == (0, 3)
+    one = np.array([[1.0]])  # a single cell that lists itself
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(one), oracle.parallel(one))
+    two = np.array([[2.0], [1.0]])
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(two), oracle.parallel(two))
+
+
+def test_banners(cuda, capsys):
+    idx = np.array([[2.0, 3.0], [1.0, 3.0], [1.0, 2.0]])
+    cuda.rcpp_parallel_jaccard_coef(idx, True)
+    assert capsys.readouterr().out == "Running Parallell Jaccard Coefficient Estimation...\nDone!!\n"
+    cuda.jaccard_coeff(idx, True)
+    assert capsys.readouterr().out == "Running Jaccard Coefficient Estimation...\n"
+
+
+def test_pinned_buffers_and_out_argument(cuda, oracle):
+    idx0 = synth.knn_index(20000, 30, seed=5)
+    r = synth.to_r_matrix(idx0)
+    pin_in = cuda.pinned_empty(r.shape)
+    pin_in[...] = r
+    pin_out = cuda.pinned_empty((r.size, 3))
+    pin_out[...] = -1.0  # must be fully overwritten
+    res = cuda.rcpp_parallel_jaccard_coef(pin_in, out=pin_out)
+    assert res is pin_out
+    assert np.array_equal(np.asarray(res), oracle.parallel(r))
+
+
+def test_config1_10k_k15(cuda, oracle):
+    """BASELINE.json configs[0]: 10k cells, k=15."""
+    r = synth.to_r_matrix(synth.knn_index(10_000, 15))
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(r), oracle.parallel(r))
+    assert np.array_equal(cuda.jaccard_coeff(r), oracle.serial(r))
+
+
+@pytest.mark.parametrize("family,scramble", [("planted", False), ("planted", True), ("uniform", False)])
+def test_config2_100k_k30(cuda, oracle, family, scramble):
+    """BASELINE.json configs[1]: 100k cells, k=30 (E = 3e6): whole-matrix memcmp."""
+    r = synth.to_r_matrix(synth.knn_index(100_000, 30, family=family, scramble=scramble))
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(r), oracle.parallel(r))
+
+
+def test_phenograph_edges_call_site(cuda, oracle):
+    """R/clustCells.R:63-66: drop the self column, weight, keep weight > 0."""
+    idx0 = synth.knn_index(5000, 15)
+    neigh = np.concatenate([np.arange(1, 5001)[:, None], idx0.numpy() + 1], axis=1)  # col 1 = self
+    rel = cuda.phenograph_edges(neigh)
+    full = oracle.parallel(synth.to_r_matrix(idx0))
+    assert np.array_equal(rel, full[full[:, 2] > 0])
+
+
+def test_device_entry_points(cuda, oracle):
+    """Resident-data path: pad -> fused kernel; counts -> expand (both modes); exact kernel."""
+    from gficf_b200 import device as D
+
+    n, k = 30_000, 30
+    idx0 = synth.knn_index(n, k, scramble=True)
+    r = synth.to_r_matrix(idx0)
+    want = oracle.parallel(r)
+    d_dense = idx0.cuda()
+    padded, flags = D.pad_rows(d_dense)
+    assert padded.shape == (n, 32) and int(flags[0]) == 0
+    assert torch.equal(padded[:, :k], d_dense) and bool((padded[:, k:] == -2).all())
+    # the f64 column-major route gives the same padded matrix
+    d_r = torch.from_numpy(np.ascontiguousarray(r.T)).cuda()  # (k, n) C-order == column-major n x k
+    padded2, flags2 = D.layout_from_r_matrix(d_r, n, k)
+    assert torch.equal(padded, padded2) and int(flags2[0]) == 0
+    out, flags = D.jaccard_edges(padded, n, k)
+    torch.cuda.synchronize()
+    assert int(flags[0]) == 0
+    assert np.array_equal(out.cpu().numpy().T, want)
+    # a slab
+    lo, hi = 1234, 20_001
+    out_s, _ = D.jaccard_edges(padded, n, k, lo, hi)
+    assert np.array_equal(out_s.cpu().numpy().T, want[lo * k:hi * k])
+    # counts + expand, fixed and compacted
+    cnt, _ = D.jaccard_counts(padded, n, k)
+    exp0, _ = D.expand(padded, k, cnt, mode=0)
+    assert np.array_equal(exp0.cpu().numpy().T, want)
+    exp1, nw = D.expand(padded, k, cnt, mode=1)
+    ser = oracle.serial(r)
+    assert int(nw[0]) == int((ser[:, 2] > 0).sum())
+    assert np.array_equal(exp1.cpu().numpy().T, ser)
+    # exact kernel agrees with the fast one on clean input
+    ex = D.jaccard_counts_exact(padded, n, k, set_semantics=False, row_lo=0, row_hi=2000)
+    assert torch.equal(ex, cnt[: 2000 * k])
+
+
+def test_weight_division_matches_host_for_all_u(cuda):
+    """w = u/(2.0*k - u) computed on the device is the host's IEEE double for every (k,u)."""
+    from gficf_b200 import device as D
+
+    for k in (1, 3, 15, 30, 100, 255):
+        n = k + 1
+        idx = torch.arange(n, dtype=torch.int32)[:, None].repeat(1, k)
+        idx = ((idx + torch.arange(1, k + 1, dtype=torch.int32)[None, :]) % n).cuda().contiguous()
+        padded, _ = D.pad_rows(idx)
+        cnt = (torch.arange(n * k, dtype=torch.int64) % (k + 1)).to(torch.uint8).cuda()
+        out, _ = D.expand(padded, k, cnt, mode=0)
+        w = out[2].cpu().numpy()
+        u = cnt.cpu().numpy().astype(np.int64)
+        assert np.array_equal(w, u / (2.0 * k - u))
