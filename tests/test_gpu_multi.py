@@ -1,0 +1,95 @@
+"""GPU (-m gpu), needs >= 2 devices (skipped on a 1-GPU box; run with `gpurun --gpus 2`):
+row sharding inside ONE process through the C ABI (n_devices = 2, 4, ...: NCCL all-gather of the
+index slabs, every GPU returns its own edge slab) and one process per GPU over torch.distributed
+(gficf_b200.sharding)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from gficf_b200 import synth
+from tests.conftest import random_knn
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ndev(cuda):
+    return cuda.lib().gficf_cuda_device_count()
+
+
+@pytest.mark.parametrize("n,k", [(100_000, 30), (10_001, 15), (3_000, 100), (7, 3)])
+def test_in_process_row_sharding(cuda, oracle, n, k):
+    nd = _ndev(cuda)
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = synth.to_r_matrix(synth.knn_index(n, k, scramble=True)) if n > k + 1 else \
+        random_knn(np.random.default_rng(0), n, k, with_self=True)
+    want = oracle.parallel(r)
+    for d in sorted({2, nd}):
+        got = cuda.rcpp_parallel_jaccard_coef(r, False, d)
+        assert np.array_equal(got, want), "n_devices=%d" % d
+    # repeated ids on a slab other than the first: the exact path must run on every device
+    r2 = r.copy()
+    r2[n - 1, 0] = r2[n - 1, k - 1]
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(r2, False, 2), oracle.parallel(r2))
+    # invalid id on the last slab
+    r3 = r.copy()
+    r3[n - 1, 0] = n + 5
+    with pytest.raises(cuda.GficfCudaError):
+        cuda.rcpp_parallel_jaccard_coef(r3, False, 2)
+
+
+def test_set_devices_default(cuda, oracle):
+    if _ndev(cuda) < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = synth.to_r_matrix(synth.knn_index(50_000, 30))
+    cuda.set_devices(2)
+    try:
+        got = cuda.rcpp_parallel_jaccard_coef(r)  # n_devices=0 -> the configured default
+    finally:
+        cuda.set_devices(1)
+    assert np.array_equal(got, oracle.parallel(r))
+
+
+_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+import gficf_b200
+from gficf_b200 import sharding, synth
+from oracle.binding import Oracle
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+for n, k, dup in ((200_000, 30, False), (10_001, 15, False), (5_000, 100, False), (20_000, 30, True)):
+    r = None
+    if rank == 0:
+        r = synth.to_r_matrix(synth.knn_index(n, k, scramble=True))
+        if dup:
+            r[n - 1, 0] = r[n - 1, k - 1]
+    out = sharding.rcpp_parallel_jaccard_coef_sharded(r, n, k)
+    if rank == 0:
+        want = Oracle().parallel(r)
+        assert np.array_equal(out, want), (n, k)
+    else:
+        assert out is None
+dist.barrier()
+if rank == 0:
+    print("SHARDED_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_one_process_per_gpu_nccl(cuda, tmp_path):
+    nd = _ndev(cuda)
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(nd, 4)),
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "SHARDED_OK" in out.stdout
