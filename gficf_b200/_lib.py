@@ -6,7 +6,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libgficf_cuda.so")
+# GFICF_CUDA_LIB selects another build of the SAME library (A/B tuning variants); never a fallback
+_SO = os.environ.get("GFICF_CUDA_LIB") or os.path.join(_HERE, "libgficf_cuda.so")
 _lib = None
 
 E_NAMES = {1: "GFICF_E_ARG", 2: "GFICF_E_RANGE", 3: "GFICF_E_CUDA", 4: "GFICF_E_NCCL", 5: "GFICF_E_LIMIT"}

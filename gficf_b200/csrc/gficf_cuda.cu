@@ -99,11 +99,10 @@ int32_t row_stride(int32_t k) {
   return (k + 7) / 8 * 8;
 }
 
-int wide_log_ts(int k) { return k <= 48 ? 10 : (k <= 64 ? 11 : 12); }
+// table slots ~ k^2/2: a multiplier is collision free with probability >= ~0.37
+int wide_log_ts(int k) { return k <= 45 ? 10 : (k <= 64 ? 11 : (k <= 90 ? 12 : 13)); }
 
-size_t wide_smem_bytes(int log_ts) {
-  return (size_t)kWideWarps * ((1u << log_ts) + 256) * 4 + 129 * sizeof(double);
-}
+size_t wide_smem_bytes(int log_ts) { return (size_t)wide_smem_words(log_ts) * 4 + 129 * sizeof(double); }
 
 // persistent grid: resident CTAs per SM x SM count, capped by the work
 template <typename K>
@@ -140,7 +139,7 @@ void launch_wide(const int* idx, int k, int kp, long long lo, long long hi, doub
     attr_set[dev & 63] = true;
   }
   const int block = kWideWarps * 32;
-  const int grid = persistent_grid(kern, block, smem, (hi - lo + kWideWarps - 1) / kWideWarps);
+  const int grid = persistent_grid(kern, block, smem, hi - lo);
   kern<<<grid, block, smem, st>>>(idx, k, kp, lo, hi, f, t, w, u, flags);
   tl_launch = {grid, block, (int)smem, 1000 + LOG_TS};
 }
@@ -159,7 +158,8 @@ bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, d
     switch (wide_log_ts(k)) {
       case 10: launch_wide<10, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
       case 11: launch_wide<11, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
-      default: launch_wide<12, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
+      case 12: launch_wide<12, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
+      default: launch_wide<13, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
     }
   } else {
     return false;
@@ -437,78 +437,97 @@ void d2h_run(DeviceWs& ws, double* dst, const double* src, long long count, cuda
 
 struct SlabResult {
   unsigned flags = 0;
-  long long n_written = 0;
+  long long n_written = -1;
   float ms_h2d = 0, ms_k0 = 0, ms_k1 = 0, ms_d2h = 0, ms_gather = 0;
   int launches = 0;
+  bool counts_ready = false;  // phase 1 left fast-kernel counts in ws.counts
   Err err;
 };
 
-// One device's share of a call: rows [lo,hi) of n.  With ndev>1 the int32 index
-// slabs are exchanged with an in-place NCCL all-gather.
-void run_device(int rank, int ndev, const double* h_idx, long long n, int k, long long rows_per,
-                double* h_out, int mode, SlabResult* res) {
-  try {
-    DeviceWs& ws = g_ws[rank];
-    CU_TRY(cudaSetDevice(rank));
-    ws.ensure(rank);
-    const int kp = row_stride(k);
-    const long long lo = std::min<long long>(n, rank * rows_per);
-    const long long hi = std::min<long long>(n, lo + rows_per);
-    const long long rows = hi - lo;
-    const long long E = n * (long long)k;
-    const long long slab_e = rows * (long long)k;
-    const int cbytes = k <= 255 ? 1 : 2;
+struct Slab {
+  int rank, ndev, k, kp, mode;
+  long long n, rows_per, lo, hi, rows, E, slab_e;
+  const double* h_idx;
+  double* h_out;
+  Slab(int rank_, int ndev_, const double* h_idx_, long long n_, int k_, long long rows_per_,
+       double* h_out_, int mode_)
+      : rank(rank_), ndev(ndev_), k(k_), kp(row_stride(k_)), mode(mode_), n(n_), rows_per(rows_per_),
+        h_idx(h_idx_), h_out(h_out_) {
+    lo = std::min<long long>(n, rank * rows_per);
+    hi = std::min<long long>(n, lo + rows_per);
+    rows = hi - lo;
+    E = n * (long long)k;
+    slab_e = rows * (long long)k;
+  }
+};
 
-    ws.in_f64.need(std::max<size_t>(16, (size_t)rows * k * sizeof(double)));
-    ws.idx.need(std::max<size_t>(16, (size_t)rows_per * ndev * kp * sizeof(int)));
+void read_small(DeviceWs& ws, SlabResult* res) {
+  CU_TRY(cudaMemcpyAsync(ws.h_small, ws.small.p, 16, cudaMemcpyDeviceToHost, ws.s_comp));
+  CU_TRY(cudaStreamSynchronize(ws.s_comp));
+  res->flags |= ws.h_small[0];
+}
+
+void d2h_slab(DeviceWs& ws, const Slab& s, SlabResult* res) {
+  double* d_from = (double*)ws.out.p;
+  double* d_to = d_from + s.slab_e;
+  double* d_w = d_to + s.slab_e;
+  CU_TRY(cudaEventRecord(ws.ev[4], ws.s_copy));
+  d2h_run(ws, s.h_out + s.lo * s.k, d_from, s.slab_e, ws.s_copy);
+  d2h_run(ws, s.h_out + s.E + s.lo * s.k, d_to, s.slab_e, ws.s_copy);
+  d2h_run(ws, s.h_out + 2 * s.E + s.lo * s.k, d_w, s.slab_e, ws.s_copy);
+  CU_TRY(cudaEventRecord(ws.ev[5], ws.s_copy));
+  CU_TRY(cudaStreamSynchronize(ws.s_copy));
+  float ms = 0;
+  CU_TRY(cudaEventElapsedTime(&ms, ws.ev[4], ws.ev[5]));
+  res->ms_d2h += ms;
+}
+
+// Phase 1 of one device's share (rows [lo,hi) of n): H2D of its rows, layout pre-pass, exchange
+// of the int32 index slabs (in-place NCCL all-gather when ndev>1), then the fast kernel:
+//   parallel export, k<=128: fused kernel in row chunks, the D2H of chunk c overlapping the
+//     kernel of chunk c+1 (the result stands unless some device raises a dup/hash flag);
+//   serial export, k<=128:   fast count kernel (the compaction happens in phase 2).
+void device_phase1(Slab s, SlabResult* res) {
+  try {
+    DeviceWs& ws = g_ws[s.rank];
+    CU_TRY(cudaSetDevice(s.rank));
+    ws.ensure(s.rank);
+    const int k = s.k;
+    const int cbytes = k <= 255 ? 1 : 2;
+    ws.in_f64.need(std::max<size_t>(16, (size_t)s.rows * k * sizeof(double)));
+    ws.idx.need(std::max<size_t>(16, (size_t)s.rows_per * s.ndev * s.kp * sizeof(int)));
+    ws.out.need(std::max<size_t>(16, (size_t)s.slab_e * 3 * sizeof(double)));
     unsigned* d_flags = (unsigned*)ws.small.p;
-    long long* d_nw = (long long*)((char*)ws.small.p + 8);
     CU_TRY(cudaMemsetAsync(ws.small.p, 0, 64, ws.s_comp));
 
-    // ---- H2D of this device's rows (all k columns), layout pre-pass
     CU_TRY(cudaEventRecord(ws.ev[0], ws.s_comp));
-    h2d_block(ws, h_idx + lo, n, (double*)ws.in_f64.p, rows, k, ws.s_comp);
+    h2d_block(ws, s.h_idx + s.lo, s.n, (double*)ws.in_f64.p, s.rows, k, ws.s_comp);
     CU_TRY(cudaEventRecord(ws.ev[1], ws.s_comp));
-    launch_layout((const double*)ws.in_f64.p, rows, lo, n, k, lo, hi, (int*)ws.idx.p, d_flags,
+    launch_layout((const double*)ws.in_f64.p, s.rows, s.lo, s.n, k, s.lo, s.hi, (int*)ws.idx.p, d_flags,
                   ws.s_comp);
-    res->launches += rows > 0;
+    res->launches += s.rows > 0;
     CU_TRY(cudaEventRecord(ws.ev[2], ws.s_comp));
-    // ---- exchange index slabs
-    if (ndev > 1) {
-      const size_t cnt = (size_t)rows_per * kp;
-      NCCL_TRY(nccl_dyn::get().AllGather((const char*)ws.idx.p + (size_t)rank * cnt * sizeof(int),
-                                         ws.idx.p, cnt, ncclInt32, g_nccl.comms[rank], ws.s_comp));
+    if (s.ndev > 1) {
+      const size_t cnt = (size_t)s.rows_per * s.kp;
+      NCCL_TRY(nccl_dyn::get().AllGather((const char*)ws.idx.p + (size_t)s.rank * cnt * sizeof(int),
+                                         ws.idx.p, cnt, ncclInt32, g_nccl.comms[s.rank], ws.s_comp));
     }
     CU_TRY(cudaEventRecord(ws.ev[3], ws.s_comp));
 
     const int* d_idx = (const int*)ws.idx.p;
     const bool fast_ok = k <= 128;
-    ws.out.need(std::max<size_t>(16, (size_t)slab_e * 3 * sizeof(double)));
     double* d_from = (double*)ws.out.p;
-    double* d_to = d_from + slab_e;
-    double* d_w = d_to + slab_e;
-    auto read_small = [&]() {
-      CU_TRY(cudaMemcpyAsync(ws.h_small, ws.small.p, 16, cudaMemcpyDeviceToHost, ws.s_comp));
-      CU_TRY(cudaStreamSynchronize(ws.s_comp));
-      res->flags |= ws.h_small[0];
-    };
-    auto front_timings = [&]() {
-      CU_TRY(cudaEventElapsedTime(&res->ms_h2d, ws.ev[0], ws.ev[1]));
-      CU_TRY(cudaEventElapsedTime(&res->ms_k0, ws.ev[1], ws.ev[2]));
-      CU_TRY(cudaEventElapsedTime(&res->ms_gather, ws.ev[2], ws.ev[3]));
-    };
-    res->n_written = -1;
-
-    if (mode == GFICF_MODE_PARALLEL && fast_ok) {
-      // fused kernel in row chunks; the D2H of chunk c overlaps the kernel of chunk c+1
+    double* d_to = d_from + s.slab_e;
+    double* d_w = d_to + s.slab_e;
+    int used = 0;
+    if (fast_ok && s.mode == GFICF_MODE_PARALLEL) {
       const int nch =
-          (int)std::min<long long>(kMaxChunks, std::max<long long>(1, slab_e * 24 / (48ll << 20)));
-      const long long rpc = (rows + nch - 1) / nch;
-      int used = 0;
+          (int)std::min<long long>(kMaxChunks, std::max<long long>(1, s.slab_e * 24 / (48ll << 20)));
+      const long long rpc = (s.rows + nch - 1) / nch;
       for (int c = 0; c < nch; ++c) {
-        const long long clo = lo + c * rpc, chi = std::min(hi, clo + rpc);
+        const long long clo = s.lo + c * rpc, chi = std::min(s.hi, clo + rpc);
         if (clo >= chi) break;
-        const long long eo = (clo - lo) * k;
+        const long long eo = (clo - s.lo) * k;
         CU_TRY(cudaEventRecord(ws.ev_k0[c], ws.s_comp));
         launch_fast<false>(d_idx, k, clo, chi, d_from + eo, d_to + eo, d_w + eo, nullptr, d_flags,
                            ws.s_comp);
@@ -520,66 +539,71 @@ void run_device(int rank, int ndev, const double* h_idx, long long n, int k, lon
       CU_TRY(cudaStreamWaitEvent(ws.s_copy, ws.ev[3], 0));
       CU_TRY(cudaEventRecord(ws.ev[4], ws.s_copy));
       for (int c = 0; c < used; ++c) {
-        const long long clo = lo + c * rpc, chi = std::min(hi, clo + rpc);
-        const long long eo = (clo - lo) * k, ce = (chi - clo) * k;
+        const long long clo = s.lo + c * rpc, chi = std::min(s.hi, clo + rpc);
+        const long long eo = (clo - s.lo) * k, ce = (chi - clo) * k;
         CU_TRY(cudaStreamWaitEvent(ws.s_copy, ws.ev_chunk[c], 0));
-        d2h_run(ws, h_out + lo * k + eo, d_from + eo, ce, ws.s_copy);
-        d2h_run(ws, h_out + E + lo * k + eo, d_to + eo, ce, ws.s_copy);
-        d2h_run(ws, h_out + 2 * E + lo * k + eo, d_w + eo, ce, ws.s_copy);
+        d2h_run(ws, s.h_out + s.lo * k + eo, d_from + eo, ce, ws.s_copy);
+        d2h_run(ws, s.h_out + s.E + s.lo * k + eo, d_to + eo, ce, ws.s_copy);
+        d2h_run(ws, s.h_out + 2 * s.E + s.lo * k + eo, d_w + eo, ce, ws.s_copy);
       }
       CU_TRY(cudaEventRecord(ws.ev[5], ws.s_copy));
-      read_small();
-      CU_TRY(cudaStreamSynchronize(ws.s_copy));
-      front_timings();
-      for (int c = 0; c < used; ++c) {
-        float ms = 0;
-        CU_TRY(cudaEventElapsedTime(&ms, ws.ev_k0[c], ws.ev_k1[c]));
-        res->ms_k1 += ms;
-      }
-      CU_TRY(cudaEventElapsedTime(&res->ms_d2h, ws.ev[4], ws.ev[5]));
-      if (res->flags & kFlagBadId) return;  // the caller reports GFICF_E_RANGE
-      if (!(res->flags & (kFlagDupId | kFlagHashFail))) return;
-      // a row repeats an id (or found no collision-free hash): redo with the exact kernel
-    } else {
-      read_small();
-      front_timings();
-      if (res->flags & kFlagBadId) return;
-    }
-
-    // ---- counts -> expand path: the serial export, k>128, or rows with repeated ids
-    ws.counts.need(std::max<size_t>(16, (size_t)slab_e * cbytes));
-    ws.scratch.need(expand_scratch_bytes(slab_e));
-    CU_TRY(cudaEventRecord(ws.ev[6], ws.s_comp));
-    bool exact = !fast_ok || (res->flags & (kFlagDupId | kFlagHashFail));
-    if (!exact) {
-      launch_fast<true>(d_idx, k, lo, hi, nullptr, nullptr, nullptr, (uint8_t*)ws.counts.p, d_flags,
+    } else if (fast_ok && s.slab_e > 0) {
+      ws.counts.need(std::max<size_t>(16, (size_t)s.slab_e * cbytes));
+      CU_TRY(cudaEventRecord(ws.ev_k0[0], ws.s_comp));
+      launch_fast<true>(d_idx, k, s.lo, s.hi, nullptr, nullptr, nullptr, (uint8_t*)ws.counts.p, d_flags,
                         ws.s_comp);
+      CU_TRY(cudaEventRecord(ws.ev_k1[0], ws.s_comp));
       res->launches++;
-      read_small();
-      exact = (res->flags & (kFlagDupId | kFlagHashFail)) != 0;
+      res->counts_ready = true;
     }
-    if (exact) {
-      launch_exact(d_idx, k, lo, hi, mode == GFICF_MODE_SERIAL ? 1 : 0, ws.counts.p, ws.s_comp);
+    read_small(ws, res);
+    CU_TRY(cudaStreamSynchronize(ws.s_copy));
+    CU_TRY(cudaEventElapsedTime(&res->ms_h2d, ws.ev[0], ws.ev[1]));
+    CU_TRY(cudaEventElapsedTime(&res->ms_k0, ws.ev[1], ws.ev[2]));
+    CU_TRY(cudaEventElapsedTime(&res->ms_gather, ws.ev[2], ws.ev[3]));
+    for (int c = 0; c < std::max(used, res->counts_ready ? 1 : 0); ++c) {
+      float ms = 0;
+      CU_TRY(cudaEventElapsedTime(&ms, ws.ev_k0[c], ws.ev_k1[c]));
+      res->ms_k1 += ms;
+    }
+    if (used) CU_TRY(cudaEventElapsedTime(&res->ms_d2h, ws.ev[4], ws.ev[5]));
+  } catch (const Err& e) {
+    res->err = e;
+  }
+}
+
+// Phase 2 (only when needed): counts -> expand -> D2H.  `exact` is decided from the flags of
+// ALL devices: a row with a repeated id invalidates the fast count of every edge that targets
+// it, whichever device owns that edge.
+void device_phase2(Slab s, bool exact, SlabResult* res) {
+  try {
+    DeviceWs& ws = g_ws[s.rank];
+    CU_TRY(cudaSetDevice(s.rank));
+    if (s.slab_e <= 0) return;
+    const int k = s.k;
+    const int cbytes = k <= 255 ? 1 : 2;
+    const int* d_idx = (const int*)ws.idx.p;
+    double* d_from = (double*)ws.out.p;
+    double* d_to = d_from + s.slab_e;
+    double* d_w = d_to + s.slab_e;
+    long long* d_nw = (long long*)((char*)ws.small.p + 8);
+    ws.counts.need(std::max<size_t>(16, (size_t)s.slab_e * cbytes));
+    ws.scratch.need(expand_scratch_bytes(s.slab_e));
+    CU_TRY(cudaEventRecord(ws.ev[6], ws.s_comp));
+    if (exact || !res->counts_ready) {
+      launch_exact(d_idx, k, s.lo, s.hi, s.mode == GFICF_MODE_SERIAL ? 1 : 0, ws.counts.p, ws.s_comp);
       res->launches++;
     }
-    launch_expand(d_idx, k, lo, hi, ws.counts.p, mode, d_from, d_to, d_w, ws.scratch.p, d_nw,
+    launch_expand(d_idx, k, s.lo, s.hi, ws.counts.p, s.mode, d_from, d_to, d_w, ws.scratch.p, d_nw,
                   ws.s_comp);
-    res->launches += mode == GFICF_MODE_SERIAL ? 4 : 1;
+    res->launches += s.mode == GFICF_MODE_SERIAL ? 4 : 1;
     CU_TRY(cudaEventRecord(ws.ev[7], ws.s_comp));
-    read_small();
-    if (mode == GFICF_MODE_SERIAL) res->n_written = *(long long*)((char*)ws.h_small + 8);
+    read_small(ws, res);
+    if (s.mode == GFICF_MODE_SERIAL) res->n_written = *(long long*)((char*)ws.h_small + 8);
     float ms = 0;
     CU_TRY(cudaEventElapsedTime(&ms, ws.ev[6], ws.ev[7]));
     res->ms_k1 += ms;
-    CU_TRY(cudaEventRecord(ws.ev[4], ws.s_copy));
-    d2h_run(ws, h_out + lo * k, d_from, slab_e, ws.s_copy);
-    d2h_run(ws, h_out + E + lo * k, d_to, slab_e, ws.s_copy);
-    d2h_run(ws, h_out + 2 * E + lo * k, d_w, slab_e, ws.s_copy);
-    CU_TRY(cudaEventRecord(ws.ev[5], ws.s_copy));
-    CU_TRY(cudaStreamSynchronize(ws.s_copy));
-    float ms2 = 0;
-    CU_TRY(cudaEventElapsedTime(&ms2, ws.ev[4], ws.ev[5]));
-    res->ms_d2h += ms2;
+    d2h_slab(ws, s, res);
   } catch (const Err& e) {
     res->err = e;
   }
@@ -709,21 +733,42 @@ int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int
   const auto t0 = std::chrono::steady_clock::now();
   const long long rows_per = (n + ndev - 1) / ndev;
   std::vector<SlabResult> res(ndev);
+  std::vector<Slab> slabs;
+  for (int r = 0; r < ndev; ++r) slabs.emplace_back(r, ndev, idx, (long long)n, (int)k, rows_per, out, (int)mode);
+  auto first_error = [&]() {
+    for (auto& r : res)
+      if (r.err.code != GFICF_OK) throw r.err;
+  };
   if (ndev == 1) {
-    run_device(0, 1, idx, n, k, rows_per, out, mode, &res[0]);
+    device_phase1(slabs[0], &res[0]);
   } else {
     nccl_ensure(ndev);
     std::vector<std::thread> th;
-    for (int r = 0; r < ndev; ++r)
-      th.emplace_back(run_device, r, ndev, idx, (long long)n, (int)k, rows_per, out, (int)mode, &res[r]);
+    for (int r = 0; r < ndev; ++r) th.emplace_back(device_phase1, slabs[r], &res[r]);
     for (auto& t : th) t.join();
+  }
+  unsigned all_flags = 0;
+  for (auto& r : res) all_flags |= r.flags;
+  bool bad_id = (all_flags & kFlagBadId) != 0;
+  if (!bad_id) {
+    first_error();
+    const bool exact = k > 128 || (all_flags & (kFlagDupId | kFlagHashFail));
+    if (exact || mode == GFICF_MODE_SERIAL) {
+      if (ndev == 1) {
+        device_phase2(slabs[0], exact, &res[0]);
+      } else {
+        std::vector<std::thread> th;
+        for (int r = 0; r < ndev; ++r) th.emplace_back(device_phase2, slabs[r], exact, &res[r]);
+        for (auto& t : th) t.join();
+      }
+    }
   }
   cudaSetDevice(prev_dev);
   const auto t1 = std::chrono::steady_clock::now();
   unsigned flags = 0;
   double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (auto& r : res) {
-    if (r.err.code != GFICF_OK) throw r.err;
+    if (!bad_id && r.err.code != GFICF_OK) throw r.err;
     flags |= r.flags;
     tm[0] = std::max<double>(tm[0], r.ms_h2d);
     tm[1] = std::max<double>(tm[1], r.ms_k0);

@@ -28,6 +28,14 @@
 //     output does not evict the index matrix from L2.
 #pragma once
 #include <cuda_runtime.h>
+
+// tuning knobs (overridable with -D for A/B runs; defaults are the measured best)
+#ifndef GFICF_SMALL_LOG_TS32
+#define GFICF_SMALL_LOG_TS32 9   // hash-table slots per warp for 16 < k <= 32: 2^9
+#endif
+#ifndef GFICF_SMALL_MINB
+#define GFICF_SMALL_MINB 4       // resident CTAs per SM the k<=32 kernel is compiled for
+#endif
 #include <stdint.h>
 
 namespace gficf {
@@ -43,6 +51,52 @@ __device__ __forceinline__ unsigned next_mult(unsigned m) { return (m * 0x2C1B3C
 
 __device__ __forceinline__ int4 ldg16(const int* p) {
   return __ldg(reinterpret_cast<const int4*>(p));
+}
+
+// 16-byte piece of neighbour row t: base already points at this lane's column offset
+__device__ __forceinline__ int4 ldg_row(const char* lane_base, unsigned t, unsigned row_bytes) {
+  return __ldg(reinterpret_cast<const int4*>(lane_base + (unsigned long long)t * row_bytes));  // IMAD.WIDE.U32
+}
+
+// acc += INC when the table slot of x holds x: ISETP + predicated IADD, no select chain
+template <unsigned INC>
+__device__ __forceinline__ void add_if_eq(unsigned& acc, unsigned a, unsigned b) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}"
+      : "+r"(acc) : "r"(a), "r"(b), "n"(INC));
+}
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+  unsigned r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+
+// shared address of the table slot of id x: IMAD (multiplicative hash), SHF (top bits), and one
+// IMAD for base + 4*slot (kept opaque, otherwise it is split into a mask and an add)
+template <int SHIFT>
+__device__ __forceinline__ unsigned slot_addr(unsigned tbl32, unsigned x, unsigned mult) {
+  unsigned a;
+  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"((x * mult) >> SHIFT), "r"(tbl32));
+  return a;
+}
+
+// membership probes of the 4 ids of one 16-byte piece against a collision-free table at
+// shared address tbl32: per id IMAD (hash), SHF (slot), LEA (address), LDS, ISETP, @p IADD
+template <unsigned INC, int SHIFT>
+__device__ __forceinline__ void probe4(unsigned& acc, unsigned tbl32, unsigned mult, const int4& v) {
+  const unsigned x0 = (unsigned)v.x, x1 = (unsigned)v.y, x2 = (unsigned)v.z, x3 = (unsigned)v.w;
+  const unsigned k0 = lds_u32(slot_addr<SHIFT>(tbl32, x0, mult));
+  const unsigned k1 = lds_u32(slot_addr<SHIFT>(tbl32, x1, mult));
+  const unsigned k2 = lds_u32(slot_addr<SHIFT>(tbl32, x2, mult));
+  const unsigned k3 = lds_u32(slot_addr<SHIFT>(tbl32, x3, mult));
+  add_if_eq<INC>(acc, k0, x0);
+  add_if_eq<INC>(acc, k1, x1);
+  add_if_eq<INC>(acc, k2, x2);
+  add_if_eq<INC>(acc, k3, x3);
 }
 
 __device__ __forceinline__ double jaccard_weight(int u, int k) {
@@ -138,14 +192,14 @@ struct SmallK {
   static constexpr int EPS = 32 / LPE;
   static constexpr int S = (KP >= EPS) ? KP / EPS : 1;
   // table slots per warp: ~k^2/2 gives a >40% chance that a multiplier is collision free
-  static constexpr int TS = (KP == 32) ? 512 : (KP == 16) ? 128 : 64;
-  static constexpr int LOG_TS = (KP == 32) ? 9 : (KP == 16) ? 7 : 6;
+  static constexpr int LOG_TS = (KP == 32) ? GFICF_SMALL_LOG_TS32 : (KP == 16) ? 7 : 6;
+  static constexpr int TS = 1 << LOG_TS;
 };
 
 constexpr int kSmallWarps = 8;
 
 template <int KP, bool COUNTS_ONLY>
-__global__ void __launch_bounds__(kSmallWarps * 32, 4)
+__global__ void __launch_bounds__(kSmallWarps * 32, GFICF_SMALL_MINB)
 jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, long long row_hi,
                        double* __restrict__ o_from, double* __restrict__ o_to,
                        double* __restrict__ o_w, uint8_t* __restrict__ o_u,
@@ -164,7 +218,8 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
 
   const long long nwarps = (long long)gridDim.x * kSmallWarps;
   long long row = row_lo + (long long)blockIdx.x * kSmallWarps + warp;
-  const int sub4 = (lane % LPE) * 4;  // which 16-byte piece of a neighbour row this lane fetches
+  // which 16-byte piece of a neighbour row this lane fetches
+  const char* lane_base = reinterpret_cast<const char*>(idx + (lane % LPE) * 4);
   const int grp = lane / LPE;
   const bool valid = lane < k;
   unsigned warp_flags = 0;
@@ -182,7 +237,7 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     for (int s = 0; s < S; ++s) {
       const int e = grp * S + s;
       const int t = __shfl_sync(kFull, a, e & 31);
-      v[s] = (e < k) ? ldg16(idx + (long long)t * KP + sub4)
+      v[s] = (e < k) ? ldg_row(lane_base, (unsigned)t, KP * 4)
                      : make_int4(kPadId, kPadId, kPadId, kPadId);
     }
     // ---- collision-free hash of N(i): search a multiplier
@@ -212,17 +267,13 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     __syncwarp();
     // ---- probe the gathered ids; counts of up to 4 steps packed per register
     unsigned c_lo = 0, c_hi = 0;
+    const unsigned tbl32 = smem_addr(tbl);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const unsigned x0 = (unsigned)v[s].x, x1 = (unsigned)v[s].y, x2 = (unsigned)v[s].z,
-                     x3 = (unsigned)v[s].w;
-      unsigned h = 0;
-      h += tbl[(x0 * mult) >> SHIFT] == x0;
-      h += tbl[(x1 * mult) >> SHIFT] == x1;
-      h += tbl[(x2 * mult) >> SHIFT] == x2;
-      h += tbl[(x3 * mult) >> SHIFT] == x3;
-      if (s < 4) c_lo += h << (8 * (s & 3));
-      else c_hi += h << (8 * (s & 3));
+      if ((s & 3) == 0) probe4<1u, SHIFT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s]);
+      if ((s & 3) == 1) probe4<1u << 8, SHIFT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s]);
+      if ((s & 3) == 2) probe4<1u << 16, SHIFT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s]);
+      if ((s & 3) == 3) probe4<1u << 24, SHIFT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s]);
     }
 #pragma unroll
     for (int m = 1; m < LPE; m <<= 1) {
@@ -259,11 +310,57 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
 }
 
 // ---------------------------------------------------------------------------
-// Fast kernel, 32 < k <= 128: the whole warp fetches ONE neighbour row per load
-// instruction (lane l brings ids 4l..4l+3), U rows in flight per batch.
+// Fast kernel, 32 < k <= 128: a warp-group (one CTA of 4 warps) owns row i.
+//   * the row's ids go to shared memory once; warp 0 searches the collision-free
+//     multiplier and fills the CTA's hash table while the other warps already have
+//     their first gathers in flight (the loads do not depend on the table);
+//   * each warp takes a quarter of the row's edges; one load instruction fetches ONE
+//     neighbour row (lane l brings ids 4l..4l+3), up to U rows in flight per warp;
+//   * the table is shared by the 4 warps, so it costs 4x less shared memory per
+//     resident warp than a per-warp table: 24-48 warps per SM stay resident.
 // ---------------------------------------------------------------------------
 constexpr int kWideWarps = 4;
 constexpr int kWideU = 8;  // neighbour rows in flight per warp
+
+__host__ __device__ constexpr int wide_smem_words(int log_ts) { return (1 << log_ts) + 128 + 128 + 4; }
+
+// N neighbour rows of one batch: issue the gathers / probe them.  N is a template
+// parameter (dispatched on the warp-uniform batch size) so that both are branch-free and the
+// compiler can put all 4N shared-memory probes in flight together.
+template <int N>
+__device__ __forceinline__ void wide_load(int4 (&v)[kWideU], const char* lane_base, const int* ids,
+                                          unsigned row_bytes, bool lane_on) {
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const unsigned t = (unsigned)ids[q];
+    if (lane_on) v[q] = ldg_row(lane_base, t, row_bytes);  // lanes past the row keep their pads
+  }
+}
+
+template <int N, int SHIFT>
+__device__ __forceinline__ void wide_probe(const int4 (&v)[kWideU], unsigned tbl, unsigned mult,
+                                           unsigned& a0, unsigned& a1) {
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    if ((q & 3) == 0) probe4<1u, SHIFT>(q < 4 ? a0 : a1, tbl, mult, v[q]);
+    if ((q & 3) == 1) probe4<1u << 8, SHIFT>(q < 4 ? a0 : a1, tbl, mult, v[q]);
+    if ((q & 3) == 2) probe4<1u << 16, SHIFT>(q < 4 ? a0 : a1, tbl, mult, v[q]);
+    if ((q & 3) == 3) probe4<1u << 24, SHIFT>(q < 4 ? a0 : a1, tbl, mult, v[q]);
+  }
+}
+
+#define GFICF_WIDE_DISPATCH(cnt, CALL) \
+  switch (cnt) {                       \
+    case 8: { constexpr int N = 8; CALL; } break; \
+    case 7: { constexpr int N = 7; CALL; } break; \
+    case 6: { constexpr int N = 6; CALL; } break; \
+    case 5: { constexpr int N = 5; CALL; } break; \
+    case 4: { constexpr int N = 4; CALL; } break; \
+    case 3: { constexpr int N = 3; CALL; } break; \
+    case 2: { constexpr int N = 2; CALL; } break; \
+    case 1: { constexpr int N = 1; CALL; } break; \
+    default: break;                    \
+  }
 
 template <int LOG_TS, bool COUNTS_ONLY>
 __global__ void __launch_bounds__(kWideWarps * 32)
@@ -273,104 +370,115 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
                       unsigned* __restrict__ flags) {
   constexpr int TS = 1 << LOG_TS, SHIFT = 32 - LOG_TS;
   extern __shared__ unsigned smem_u[];
-  // per warp: table[TS] | own row ids[128] | counts[128]
-  constexpr int PER_WARP = TS + 128 + 128;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned* tbl = smem_u + warp * PER_WARP;
-  int* srow = reinterpret_cast<int*>(tbl + TS);
-  int* scnt = srow + 128;
-  double* lut = reinterpret_cast<double*>(smem_u + kWideWarps * PER_WARP);  // [129]
+  unsigned* tbl = smem_u;                             // [TS]
+  int* srow = reinterpret_cast<int*>(tbl + TS);        // [128] ids of row i
+  int* scnt = srow + 128;                              // [128] u per edge
+  unsigned* s_mult = reinterpret_cast<unsigned*>(scnt + 128);  // [4]
+  double* lut = reinterpret_cast<double*>(s_mult + 4);  // [129]
 
-  for (int x = lane; x < TS; x += 32) tbl[x] = kEmpty;
-  for (int x = threadIdx.x; x <= k; x += blockDim.x) lut[x] = jaccard_weight(x, k);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int x = tid; x < TS; x += blockDim.x) tbl[x] = kEmpty;
+  for (int x = tid; x <= k; x += blockDim.x) lut[x] = jaccard_weight(x, k);
   __syncthreads();
 
-  const long long nwarps = (long long)gridDim.x * kWideWarps;
   const int c0 = lane * 4;
   const bool lane_on = c0 < kp;
-  const int4 pad4 = make_int4(kPadId, kPadId, kPadId, kPadId);
+  const char* lane_base = reinterpret_cast<const char*>(idx + c0);
+  const unsigned row_bytes = (unsigned)kp * 4u;
+  // gathered pieces; lanes past the end of a row never load and keep these pads for good
+  int4 v[kWideU];
+#pragma unroll
+  for (int q = 0; q < kWideU; ++q) v[q] = make_int4(kPadId, kPadId, kPadId, kPadId);
+  // this warp's share of the row's edges, in nb batches of at most U
+  const int e_lo = (warp * k) / kWideWarps, e_hi = ((warp + 1) * k) / kWideWarps;
+  const int ne = e_hi - e_lo;
+  const int nb = (ne + kWideU - 1) / kWideU;
+  const int bsz = nb ? (ne + nb - 1) / nb : 0;
   unsigned warp_flags = 0;
 
-  for (long long row = row_lo + (long long)blockIdx.x * kWideWarps + warp; row < row_hi;
-       row += nwarps) {
-    const int4 a4 = lane_on ? ldg16(idx + row * (long long)kp + c0) : pad4;
-    const int av[4] = {a4.x, a4.y, a4.z, a4.w};
-    *reinterpret_cast<int4*>(srow + c0) = a4;
-    __syncwarp();
-    // ---- collision-free hash of N(i)
-    unsigned mult = kMult0;
-    unsigned slot[4];
-    bool dup = false;
-    int tries = 0;
-    for (;;) {
+  int a_next = (row_lo + blockIdx.x < row_hi && tid < kp)
+                   ? __ldg(idx + (row_lo + blockIdx.x) * (long long)kp + tid) : kPadId;
+  for (long long row = row_lo + blockIdx.x; row < row_hi; row += gridDim.x) {
+    srow[tid] = a_next;  // blockDim == 128 == capacity of srow
+    {
+      const long long nrow = row + gridDim.x;
+      a_next = (nrow < row_hi && tid < kp) ? __ldg(idx + nrow * (long long)kp + tid) : kPadId;
+    }
+    __syncthreads();
+    // ---- first batch of gathers (independent of the hash table)
+    {
+      const int cnt0 = min(bsz, ne);
+      GFICF_WIDE_DISPATCH(cnt0, wide_load<N>(v, lane_base, srow + e_lo, row_bytes, lane_on))
+    }
+    // ---- warp 0: collision-free hash of N(i); lane l owns keys l, l+32, l+64, l+96
+    if (warp == 0) {
+      int av[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        slot[c] = ((unsigned)av[c] * mult) >> SHIFT;
-        if (c0 + c < k) tbl[slot[c]] = (unsigned)(c0 + c);
-      }
-      __syncwarp();  // whichever writer survives in a slot, every other one sees it lost
-      bool coll = false;
+      for (int c = 0; c < 4; ++c) av[c] = srow[lane + 32 * c];
+      unsigned mult = kMult0, slot[4];
+      bool dup = false;
+      int tries = 0;
+      for (;;) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c0 + c < k) {
-          const int owner = (int)tbl[slot[c]];
-          const int okey = srow[owner];
-          const bool lost = owner != c0 + c;
-          coll |= lost && okey != av[c];
-          dup |= lost && okey == av[c];
+        for (int c = 0; c < 4; ++c) {
+          slot[c] = ((unsigned)av[c] * mult) >> SHIFT;
+          if (lane + 32 * c < k) tbl[slot[c]] = (unsigned)(lane + 32 * c);
         }
-      }
-      if (!__any_sync(kFull, coll)) break;
-      if (++tries == kMaxTries) {
-        warp_flags |= kFlagHashFail;
-        break;
+        __syncwarp();  // whichever writer survives in a slot, every other one sees it lost
+        bool coll = false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (lane + 32 * c < k) {
+            const int owner = (int)tbl[slot[c]];
+            const int okey = srow[owner];
+            const bool lost = owner != lane + 32 * c;
+            coll |= lost && okey != av[c];
+            dup |= lost && okey == av[c];
+          }
+        }
+        if (!__any_sync(kFull, coll)) break;
+        if (++tries == kMaxTries) {
+          warp_flags |= kFlagHashFail;
+          break;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (lane + 32 * c < k) tbl[slot[c]] = kEmpty;
+        __syncwarp();
+        mult = next_mult(mult);
       }
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        if (c0 + c < k) tbl[slot[c]] = kEmpty;
-      __syncwarp();
-      mult = next_mult(mult);
+        if (lane + 32 * c < k) tbl[slot[c]] = (unsigned)av[c];
+      if (__any_sync(kFull, dup)) warp_flags |= kFlagDupId;
+      if (lane == 0) s_mult[0] = mult;
     }
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c0 + c < k) tbl[slot[c]] = (unsigned)av[c];
-    if (__any_sync(kFull, dup)) warp_flags |= kFlagDupId;
-    __syncwarp();
+    __syncthreads();
+    const unsigned mult = s_mult[0];
+    const unsigned tbl32 = smem_addr(tbl);
 
-    // ---- batches of U neighbour rows
-    for (int e0 = 0; e0 < k; e0 += kWideU) {
-      int4 v[kWideU];
-#pragma unroll
-      for (int q = 0; q < kWideU; ++q) {
-        const int e = e0 + q;
-        v[q] = pad4;
-        if (e < k && lane_on) {
-          const int t = srow[e];
-          v[q] = ldg16(idx + (long long)t * kp + c0);
-        }
-      }
+    // ---- this warp's batches
+    for (int b = 0; b < nb; ++b) {
+      const int e0 = e_lo + b * bsz;
+      const int cnt = min(bsz, e_hi - e0);
       unsigned acc[kWideU / 4];
 #pragma unroll
       for (int q = 0; q < kWideU / 4; ++q) acc[q] = 0;
-#pragma unroll
-      for (int q = 0; q < kWideU; ++q) {
-        const unsigned x0 = (unsigned)v[q].x, x1 = (unsigned)v[q].y, x2 = (unsigned)v[q].z,
-                       x3 = (unsigned)v[q].w;
-        unsigned h = 0;
-        h += tbl[(x0 * mult) >> SHIFT] == x0;
-        h += tbl[(x1 * mult) >> SHIFT] == x1;
-        h += tbl[(x2 * mult) >> SHIFT] == x2;
-        h += tbl[(x3 * mult) >> SHIFT] == x3;
-        acc[q >> 2] += h << (8 * (q & 3));  // per byte: <= 4*32 = 128 after the reduction
+      GFICF_WIDE_DISPATCH(cnt, (wide_probe<N, SHIFT>(v, tbl32, mult, acc[0], acc[1])))
+      // next batch's gathers fly while this batch's counts are reduced
+      if (b + 1 < nb) {
+        const int n0 = e0 + bsz;
+        const int ncnt = min(bsz, e_hi - n0);
+        GFICF_WIDE_DISPATCH(ncnt, wide_load<N>(v, lane_base, srow + n0, row_bytes, lane_on))
       }
 #pragma unroll
       for (int m = 1; m < 32; m <<= 1) {
 #pragma unroll
         for (int q = 0; q < kWideU / 4; ++q) acc[q] += __shfl_xor_sync(kFull, acc[q], m);
       }
-      if (lane < kWideU && e0 + lane < k) {
+      if (lane < cnt) {
         unsigned word = acc[0];
 #pragma unroll
         for (int q = 1; q < kWideU / 4; ++q)
@@ -378,24 +486,22 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
         scnt[e0 + lane] = (int)((word >> (8 * (lane & 3))) & 0xFFu);
       }
     }
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c0 + c < k) tbl[slot[c]] = kEmpty;
-    // ---- epilogue: coalesced, lane -> edges lane, lane+32, ...
-    for (int e = lane; e < k; e += 32) {
-      const int u = scnt[e];
-      const long long r = (row - row_lo) * (long long)k + e;
+    __syncthreads();
+    // ---- epilogue: thread e writes edge (i, e): 8-byte coalesced streaming stores
+    if (tid < k) {
+      const int u = scnt[tid];
+      const long long r = (row - row_lo) * (long long)k + tid;
       if (COUNTS_ONLY) {
         o_u[r] = (uint8_t)u;
       } else {
         const bool nz = u > 0;
         __stcs(o_from + r, nz ? (double)(row + 1) : 0.0);
-        __stcs(o_to + r, nz ? (double)(srow[e] + 1) : 0.0);
+        __stcs(o_to + r, nz ? (double)(srow[tid] + 1) : 0.0);
         __stcs(o_w + r, lut[u]);
       }
+      tbl[((unsigned)srow[tid] * mult) >> SHIFT] = kEmpty;  // leave the table empty
     }
-    __syncwarp();
+    __syncthreads();
   }
   if (warp_flags && lane == 0) atomicOr(flags, warp_flags);
 }
