@@ -28,6 +28,8 @@
 #include <cstring>
 #include <iterator>
 #include <memory>
+#include <stdexcept>
+#include <string>
 #include <unordered_set>
 #include <vector>
 
@@ -54,7 +56,24 @@ inline void Rprintf(const char* fmt, ...) {
     fwrite(buf, 1, (size_t)m, stdout);
 }
 
+typedef std::ptrdiff_t R_xlen_t;
+
 namespace Rcpp {
+
+// Rcpp::stop(fmt, ...): raises an R error; here a C++ exception the harness catches.
+// (Not used by the reference sources; used by the drop-in bodies in gficf_b200/rpkg/src
+// when tests compile them against this stand-in.)
+struct exception : public std::runtime_error {
+  explicit exception(const std::string& m) : std::runtime_error(m) {}
+};
+inline void stop(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw exception(buf);
+}
 
 struct Placeholder {};
 static const Placeholder _ = Placeholder();

@@ -1,0 +1,51 @@
+// tests/rpkg_entry.cpp -- TEST HARNESS.  C entry points around the drop-in R-package sources
+// (gficf_b200/rpkg/src/*.cpp), compiled against the stand-in R runtime of oracle/rshim/ and
+// linked with the product library, so the exact files a maintainer would put into gficf's src/
+// are exercised end to end (R itself is not installed here).
+#include <Rcpp.h>
+
+#include <cstring>
+#include <string>
+
+Rcpp::NumericMatrix rcpp_parallel_jaccard_coef(Rcpp::NumericMatrix mat, bool printOutput);
+Rcpp::NumericMatrix jaccard_coeff(Rcpp::NumericMatrix idx, bool printOutput);
+int gficf_cuda_devices(int n);
+int gficf_cuda_visible_devices();
+
+static std::vector<char> g_sink;
+
+extern "C" {
+
+// which: 0 = rcpp_parallel_jaccard_coef, 1 = jaccard_coeff.  Returns 0, or 1 with the R error text.
+int rpkg_call(int which, const double* idx, int n, int k, double* out, int print_output, char* err,
+              int errlen, char* printed, int printedlen) {
+  g_sink.clear();
+  rshim::printf_sink() = &g_sink;
+  int rc = 0;
+  try {
+    Rcpp::NumericMatrix mat = Rcpp::NumericMatrix::wrap_external(const_cast<double*>(idx), n, k);
+    Rcpp::NumericMatrix res = which == 0 ? rcpp_parallel_jaccard_coef(mat, print_output != 0)
+                                         : jaccard_coeff(mat, print_output != 0);
+    std::memcpy(out, res.begin(), sizeof(double) * 3 * (size_t)n * (size_t)k);
+  } catch (const std::exception& e) {
+    snprintf(err, errlen, "%s", e.what());
+    rc = 1;
+  }
+  rshim::printf_sink() = nullptr;
+  int m = (int)g_sink.size() < printedlen - 1 ? (int)g_sink.size() : printedlen - 1;
+  if (printed && printedlen > 0) {
+    std::memcpy(printed, g_sink.data(), m);
+    printed[m] = 0;
+  }
+  return rc;
+}
+
+int rpkg_devices(int n) {
+  try {
+    return gficf_cuda_devices(n);
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
+int rpkg_visible_devices() { return gficf_cuda_visible_devices(); }
+}
