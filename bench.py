@@ -309,23 +309,47 @@ def run_ours(a):
                    "ms_per_step": dt * 1e3, "call": "gficf_b200.rcpp_parallel_jaccard_coef (pinned host buffers)",
                    "breakdown_ms": {kk: round(v, 3) for kk, v in tm.items() if kk != "reserved"}}
         else:
-            r_host = out_host = None
+            # one process per GPU on SHARED host matrices: every rank moves its own rows over its
+            # own PCIe link (gficf_cuda_jaccard_rank); rank 0 owns / fills / checks the matrices
+            from gficf_b200 import multiproc
+
+            multiproc.comm_init_from_torch()
+            tag = [("gficf_bench_%d_%d" % (os.getpid(), int(time.time()))) if rank == 0 else None]
+            dist.broadcast_object_list(tag, src=0)
+            r_sh = out_sh = None
             if rank == 0:
-                r_host = gficf_b200.pinned_empty((n, k))
-                r_host[...] = synth.to_r_matrix(idx0)
-                out_host = gficf_b200.pinned_empty((E, 3))
+                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=True)
+                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=True)
+                r_sh.array[...] = synth.to_r_matrix(idx0)
+            dist.barrier()
+            if rank != 0:
+                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=False)
+                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=False)
             for _ in range(2):
-                sharding.rcpp_parallel_jaccard_coef_sharded(r_host, n, k, out=out_host)
+                multiproc.rcpp_parallel_jaccard_coef_rank(r_sh.array, out_sh.array)
             barrier()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                sharding.rcpp_parallel_jaccard_coef_sharded(r_host, n, k, out=out_host)
+                multiproc.rcpp_parallel_jaccard_coef_rank(r_sh.array, out_sh.array)
             barrier()
             dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             e2e = {"value": E / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": 8 * E,
                    "d2h_bytes_per_step": 24 * E, "ms_per_step": float(dt[0]) * 1e3,
-                   "call": "gficf_b200.sharding.rcpp_parallel_jaccard_coef_sharded (host rank 0, pinned)"}
+                   "call": "gficf_b200.multiproc.rcpp_parallel_jaccard_coef_rank (one rank per GPU, shared "
+                           "page-locked host matrices; each rank moves its own row slab)",
+                   "pinned": bool(r_sh.pinned and out_sh.pinned),
+                   "breakdown_ms_rank0": {kk: round(v, 3) for kk, v in gficf_b200.last_timings().items()
+                                          if kk != "reserved"}}
+            if rank == 0:
+                # the shared result must be the single-GPU result
+                chk = out[:, : 3000 * k].cpu().numpy().T
+                e2e["matches_device_path_on_sample"] = bool(np.array_equal(out_sh.array[: 3000 * k], chk)) and \
+                    bool(np.array_equal(out_sh.array[E - 3000 * k:], out[:, E - 3000 * k:].cpu().numpy().T))
+            barrier()
+            r_sh.close()
+            out_sh.close()
+            multiproc.comm_destroy()
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None

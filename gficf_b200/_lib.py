@@ -24,8 +24,14 @@ PROTOTYPES = {
     "gficf_cuda_device_count": (C.c_int, []),
     "gficf_cuda_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "gficf_cuda_host_free": (C.c_int, [_vp]),
+    "gficf_cuda_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "gficf_cuda_host_unregister": (C.c_int, [_vp]),
     "gficf_cuda_release": (C.c_int, []),
     "gficf_cuda_last_timings": (C.c_int, [_dp]),
+    "gficf_cuda_comm_unique_id": (C.c_int, [_vp]),
+    "gficf_cuda_comm_init_rank": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_size_t]),
+    "gficf_cuda_comm_destroy": (C.c_int, []),
+    "gficf_cuda_jaccard_rank": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_char_p, C.c_size_t]),
     "gficf_cuda_row_stride": (C.c_int32, [C.c_int32]),
     "gficf_cuda_layout_dev": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
                                         C.c_int64, _vp, _vp, _vp]),

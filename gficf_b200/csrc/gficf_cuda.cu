@@ -343,6 +343,17 @@ struct NcclState {
   ncclComm_t comms[kMaxDevices] = {};
 } g_nccl;
 
+// one process per GPU: the communicator built from a unique id the host framework distributes
+struct MpState {
+  ncclComm_t comm = nullptr;
+  int nranks = 0, rank = 0, dev = 0;
+} g_mp;
+
+void mp_release() {
+  if (g_mp.comm) nccl_dyn::get().CommDestroy(g_mp.comm);
+  g_mp = MpState();
+}
+
 void nccl_release() {
   if (g_nccl.ndev) {
     for (int i = 0; i < g_nccl.ndev; ++i)
@@ -446,13 +457,15 @@ struct SlabResult {
 
 struct Slab {
   int rank, ndev, k, kp, mode;
+  int dev;                    // CUDA device ordinal (== rank inside one process)
+  ncclComm_t comm = nullptr;  // communicator of this rank when ndev > 1
   long long n, rows_per, lo, hi, rows, E, slab_e;
   const double* h_idx;
   double* h_out;
   Slab(int rank_, int ndev_, const double* h_idx_, long long n_, int k_, long long rows_per_,
        double* h_out_, int mode_)
-      : rank(rank_), ndev(ndev_), k(k_), kp(row_stride(k_)), mode(mode_), n(n_), rows_per(rows_per_),
-        h_idx(h_idx_), h_out(h_out_) {
+      : rank(rank_), ndev(ndev_), k(k_), kp(row_stride(k_)), mode(mode_), dev(rank_), n(n_),
+        rows_per(rows_per_), h_idx(h_idx_), h_out(h_out_) {
     lo = std::min<long long>(n, rank * rows_per);
     hi = std::min<long long>(n, lo + rows_per);
     rows = hi - lo;
@@ -489,9 +502,9 @@ void d2h_slab(DeviceWs& ws, const Slab& s, SlabResult* res) {
 //   serial export, k<=128:   fast count kernel (the compaction happens in phase 2).
 void device_phase1(Slab s, SlabResult* res) {
   try {
-    DeviceWs& ws = g_ws[s.rank];
-    CU_TRY(cudaSetDevice(s.rank));
-    ws.ensure(s.rank);
+    DeviceWs& ws = g_ws[s.dev];
+    CU_TRY(cudaSetDevice(s.dev));
+    ws.ensure(s.dev);
     const int k = s.k;
     const int cbytes = k <= 255 ? 1 : 2;
     ws.in_f64.need(std::max<size_t>(16, (size_t)s.rows * k * sizeof(double)));
@@ -510,7 +523,7 @@ void device_phase1(Slab s, SlabResult* res) {
     if (s.ndev > 1) {
       const size_t cnt = (size_t)s.rows_per * s.kp;
       NCCL_TRY(nccl_dyn::get().AllGather((const char*)ws.idx.p + (size_t)s.rank * cnt * sizeof(int),
-                                         ws.idx.p, cnt, ncclInt32, g_nccl.comms[s.rank], ws.s_comp));
+                                         ws.idx.p, cnt, ncclInt32, s.comm, ws.s_comp));
     }
     CU_TRY(cudaEventRecord(ws.ev[3], ws.s_comp));
 
@@ -577,8 +590,8 @@ void device_phase1(Slab s, SlabResult* res) {
 // it, whichever device owns that edge.
 void device_phase2(Slab s, bool exact, SlabResult* res) {
   try {
-    DeviceWs& ws = g_ws[s.rank];
-    CU_TRY(cudaSetDevice(s.rank));
+    DeviceWs& ws = g_ws[s.dev];
+    CU_TRY(cudaSetDevice(s.dev));
     if (s.slab_e <= 0) return;
     const int k = s.k;
     const int cbytes = k <= 255 ? 1 : 2;
@@ -683,9 +696,28 @@ int gficf_cuda_host_free(void* p) {
   return GFICF_OK;
 }
 
+int gficf_cuda_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return GFICF_E_ARG;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return GFICF_E_CUDA;
+  }
+  return GFICF_OK;
+}
+
+int gficf_cuda_host_unregister(void* p) {
+  if (!p) return GFICF_OK;
+  if (cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return GFICF_E_CUDA;
+  }
+  return GFICF_OK;
+}
+
 int gficf_cuda_release(void) {
   std::lock_guard<std::mutex> lk(g_call_mu);
   nccl_release();
+  mp_release();
   for (auto& w : g_ws) w.release();
   return GFICF_OK;
 }
@@ -743,6 +775,7 @@ int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int
     device_phase1(slabs[0], &res[0]);
   } else {
     nccl_ensure(ndev);
+    for (int r = 0; r < ndev; ++r) slabs[r].comm = g_nccl.comms[r];
     std::vector<std::thread> th;
     for (int r = 0; r < ndev; ++r) th.emplace_back(device_phase1, slabs[r], &res[r]);
     for (auto& t : th) t.join();
@@ -783,6 +816,99 @@ int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int
     throw Err{GFICF_E_RANGE,
               "neighbour ids must be integers in [1, nrow] (NaN, fractional or out-of-range id found)"};
   if (n_written) *n_written = res[0].n_written;
+  return GFICF_OK;
+  API_END
+}
+
+// ---------------------------------------------------------------- one process per GPU
+int gficf_cuda_comm_unique_id(void* id128) {
+  char* err = nullptr;
+  size_t errlen = 0;
+  API_BEGIN
+  if (!id128) return GFICF_E_ARG;
+  if (!nccl_dyn::get().ok) return GFICF_E_NCCL;
+  static_assert(sizeof(ncclUniqueId) == GFICF_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_TRY(nccl_dyn::get().GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return GFICF_OK;
+  API_END
+}
+
+int gficf_cuda_comm_init_rank(const void* id128, int32_t nranks, int32_t rank, int32_t device,
+                              char* err, size_t errlen) {
+  API_BEGIN
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks || device < 0 || device >= kMaxDevices)
+    throw Err{GFICF_E_ARG, "bad communicator arguments"};
+  if (!nccl_dyn::get().ok) throw Err{GFICF_E_NCCL, "cannot load libnccl.so.2: " + nccl_dyn::get().why};
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  mp_release();
+  CU_TRY(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NCCL_TRY(nccl_dyn::get().CommInitRank(&g_mp.comm, nranks, id, rank));
+  g_mp.nranks = nranks;
+  g_mp.rank = rank;
+  g_mp.dev = device;
+  return GFICF_OK;
+  API_END
+}
+
+int gficf_cuda_comm_destroy(void) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  mp_release();
+  return GFICF_OK;
+}
+
+int gficf_cuda_jaccard_rank(const double* idx, int64_t n, int32_t k, double* out, char* err,
+                            size_t errlen) {
+  API_BEGIN
+  if (err && errlen) err[0] = 0;
+  if (!g_mp.comm) throw Err{GFICF_E_ARG, "gficf_cuda_comm_init_rank has not been called"};
+  if (n < 0 || k < 0) throw Err{GFICF_E_ARG, "negative matrix dimension"};
+  if (n == 0 || k == 0) return GFICF_OK;
+  if (!idx || !out) throw Err{GFICF_E_ARG, "null matrix pointer"};
+  if (n >= 0x7fffffffLL - 2 || (long double)n * k >= 2147483647.0L)
+    throw Err{GFICF_E_LIMIT, "n*k must stay below 2^31 (the reference's int row index)"};
+  if (k > 65535) throw Err{GFICF_E_LIMIT, "k above 65535 is not supported"};
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int nr = g_mp.nranks;
+  const long long rows_per = (n + nr - 1) / nr;
+  Slab s(g_mp.rank, nr, idx, (long long)n, (int)k, rows_per, out, GFICF_MODE_PARALLEL);
+  s.dev = g_mp.dev;
+  s.comm = g_mp.comm;
+  SlabResult res;
+  device_phase1(s, &res);
+  // flags of all ranks (every rank must reach this collective, error or not)
+  DeviceWs& ws = g_ws[s.dev];
+  unsigned all_flags = res.flags;
+  {
+    CU_TRY(cudaSetDevice(s.dev));
+    ws.ensure(s.dev);
+    int* bits = (int*)((char*)ws.small.p + 32);
+    int h[4] = {(int)(res.flags & 1u), (int)((res.flags >> 1) & 1u), (int)((res.flags >> 2) & 1u),
+                res.err.code != GFICF_OK};
+    CU_TRY(cudaMemcpyAsync(bits, h, sizeof h, cudaMemcpyHostToDevice, ws.s_comp));
+    NCCL_TRY(nccl_dyn::get().AllReduce(bits, bits, 4, ncclInt32, ncclMax, s.comm, ws.s_comp));
+    CU_TRY(cudaMemcpyAsync(h, bits, sizeof h, cudaMemcpyDeviceToHost, ws.s_comp));
+    CU_TRY(cudaStreamSynchronize(ws.s_comp));
+    all_flags = (unsigned)h[0] | ((unsigned)h[1] << 1) | ((unsigned)h[2] << 2);
+    if (res.err.code != GFICF_OK) throw res.err;
+    if (h[3]) throw Err{GFICF_E_CUDA, "another rank failed"};
+  }
+  if (all_flags & kFlagBadId)
+    throw Err{GFICF_E_RANGE,
+              "neighbour ids must be integers in [1, nrow] (NaN, fractional or out-of-range id found)"};
+  if (k > 128 || (all_flags & (kFlagDupId | kFlagHashFail))) {
+    device_phase2(s, true, &res);
+    if (res.err.code != GFICF_OK) throw res.err;
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  double tm[8] = {res.ms_h2d, res.ms_k0, res.ms_k1, res.ms_d2h,
+                  std::chrono::duration<double, std::milli>(t1 - t0).count(), res.ms_gather,
+                  (double)res.launches, 0};
+  memcpy(tl_timings, tm, sizeof tm);
   return GFICF_OK;
   API_END
 }

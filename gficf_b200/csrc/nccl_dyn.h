@@ -16,6 +16,9 @@ struct Api {
   std::string why;
   void* handle = nullptr;
   ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -42,6 +45,9 @@ struct Api {
     return;                                                  \
   }
     GFICF_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+    GFICF_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    GFICF_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    GFICF_NCCL_SYM(AllReduce, "ncclAllReduce")
     GFICF_NCCL_SYM(CommDestroy, "ncclCommDestroy")
     GFICF_NCCL_SYM(AllGather, "ncclAllGather")
     GFICF_NCCL_SYM(Broadcast, "ncclBroadcast")

@@ -94,6 +94,10 @@ int gficf_cuda_device_count(void);
  * it is staged through internal pinned buffers). */
 int gficf_cuda_host_alloc(void** p, size_t bytes);
 int gficf_cuda_host_free(void* p);
+/* Page-lock memory the caller already owns (e.g. a shared-memory mapping that several
+ * ranks read their rows from / write their slabs to). */
+int gficf_cuda_host_register(void* p, size_t bytes);
+int gficf_cuda_host_unregister(void* p);
 
 /* Drop the cached device / pinned workspaces and NCCL communicators. */
 int gficf_cuda_release(void);
@@ -103,6 +107,27 @@ int gficf_cuda_release(void);
  * [3] D2H (overlapped portion included), [4] whole call wall-clock,
  * [5] index all-gather (n_devices>1), [6] kernels launched, [7] reserved. */
 int gficf_cuda_last_timings(double* ms8);
+
+/* ======================================================================== *
+ *  One process per GPU (MPI-style hosts, torchrun): every rank calls the same
+ *  function on the SAME host matrices (shared memory mapped by all ranks, or
+ *  any buffers when a rank only needs its own rows) and handles its own row slab:
+ *  H2D of its rows, layout pre-pass, NCCL all-gather of the int32 index slabs,
+ *  fused kernel, D2H of its edge slab -- so the PCIe legs of the ranks run in
+ *  parallel.  The communicator is built from an id created on one rank and
+ *  distributed by the host framework.
+ * ======================================================================== */
+#define GFICF_COMM_ID_BYTES 128
+int gficf_cuda_comm_unique_id(void* id128);
+int gficf_cuda_comm_init_rank(const void* id128, int32_t nranks, int32_t rank, int32_t device,
+                              char* err, size_t errlen);
+int gficf_cuda_comm_destroy(void);
+/* Collective over the communicator: rank r reads rows [r*ceil(n/R), ...) of
+ * idx_colmajor and writes the same rows' edges into out_colmajor (parallel-export
+ * semantics, rcpp_parallel_jaccard_coeff.cpp:24-55).  Errors (bad ids, CUDA failures)
+ * are agreed on by all ranks before anyone returns. */
+int gficf_cuda_jaccard_rank(const double* idx_colmajor, int64_t n, int32_t k, double* out_colmajor,
+                            char* err, size_t errlen);
 
 /* ======================================================================== *
  *  Device-buffer entry points (resident data: the benchmarked kernels, and

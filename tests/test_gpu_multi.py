@@ -75,6 +75,37 @@ for n, k, dup in ((200_000, 30, False), (10_001, 15, False), (5_000, 100, False)
         assert np.array_equal(out, want), (n, k)
     else:
         assert out is None
+# the library's own one-rank-per-GPU entry on shared page-locked host matrices
+from gficf_b200 import multiproc
+multiproc.comm_init_from_torch()
+for n, k, dup, bad in ((150_000, 30, False, False), (4_001, 100, False, False), (30_000, 30, True, False), (30_000, 15, False, True)):
+    tag = "gficf_test_%%d_%%d_%%d" %% (os.getppid(), n, k)
+    r_sh = out_sh = None
+    if rank == 0:
+        r_sh = multiproc.SharedHostMatrix(tag + "_idx", (n, k), create=True)
+        out_sh = multiproc.SharedHostMatrix(tag + "_out", (n * k, 3), create=True)
+        r_sh.array[...] = synth.to_r_matrix(synth.knn_index(n, k, scramble=True))
+        if dup:
+            r_sh.array[n - 1, 0] = r_sh.array[n - 1, k - 1]
+        if bad:
+            r_sh.array[n - 1, 0] = 0
+        out_sh.array[...] = -1.0
+    dist.barrier()
+    if rank != 0:
+        r_sh = multiproc.SharedHostMatrix(tag + "_idx", (n, k), create=False)
+        out_sh = multiproc.SharedHostMatrix(tag + "_out", (n * k, 3), create=False)
+    assert r_sh.pinned and out_sh.pinned
+    try:
+        multiproc.rcpp_parallel_jaccard_coef_rank(r_sh.array, out_sh.array)
+        assert not bad
+    except gficf_b200.GficfCudaError as e:
+        assert bad and e.code == 2, e      # every rank reports the bad id, whoever owns the row
+    dist.barrier()
+    if rank == 0 and not bad:
+        assert np.array_equal(out_sh.array, Oracle().parallel(np.asfortranarray(r_sh.array))), (n, k)
+    dist.barrier()
+    r_sh.close(); out_sh.close()
+multiproc.comm_destroy()
 dist.barrier()
 if rank == 0:
     print("SHARDED_OK")
