@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: how the counts reach the host rank (fused peer stores / NCCL send-recv)")
     return ap.parse_args()
 
 
@@ -204,6 +206,8 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the chunk sends must get SMs while the persistent count kernels own the GPU
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
     gficf_b200.lib()  # fail loudly now if the extension is missing
 
@@ -227,16 +231,41 @@ def run_ours(a):
             D.jaccard_edges(padded, n, k, out=out, flags=flags)
         launches_per_step = 1
     else:
-        counts_local = torch.empty(sharding.slab_rows(n, world) * k, dtype=torch.uint8, device=dev)
-        counts_all = torch.empty(sharding.slab_rows(n, world) * k * world, dtype=torch.uint8, device=dev)
+        # calibrate the uneven row split: rho = expand time per row / count time per row (this GPU)
+        m = min(n, 1_000_000)
+        cal_c = torch.empty(m * k, dtype=torch.uint8, device=dev)
+        cal_o = torch.empty((3, m * k), dtype=torch.float64, device=dev)
+        t = []
+        for fn in (lambda: D.jaccard_counts(padded, n, k, 0, m, out=cal_c, flags=flags),
+                   lambda: D.expand(padded, k, cal_c, mode=0, row_lo=0, row_hi=m, out=cal_o)):
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1) / 5)
+        del cal_c, cal_o
+        rho_t = torch.tensor([t[1] / t[0]], dtype=torch.float64, device=dev)
+        dist.broadcast(rho_t, src=0)  # every rank must use the same split
+        rho = float(rho_t[0])
         out = torch.empty((3, E), dtype=torch.float64, device=dev) if rank == 0 else None
+        counts_all = torch.empty(E, dtype=torch.uint8, device=dev)
+        if a.gather == "peer":
+            pg = sharding.PeerGather(n, k, rho=rho, chunks=4)
 
-        def step():
-            D.jaccard_counts(padded, n, k, lo, hi, out=counts_local[: (hi - lo) * k], flags=flags)
-            dist.all_gather_into_tensor(counts_all, counts_local)
-            if rank == 0:
-                D.expand(padded, k, counts_all[:E], mode=0, row_lo=0, row_hi=n, out=out)
-        launches_per_step = 2  # count kernel on every rank + expand on the host rank
+            def step():
+                pg.step(padded, out)
+        else:
+            pg = sharding.PipelinedGather(n, k, rho=rho, chunks=4)
+
+            def step():
+                pg.step(padded, counts_all, out)
+        pg.flags = flags
+        lo, hi = pg.bounds[rank]
+        launches_per_step = None  # counted by pg
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,24 +289,34 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         ev0[i].record()
-        if world == 1:
-            step()
-        else:
-            kev0[i].record()
-            D.jaccard_counts(padded, n, k, lo, hi, out=counts_local[: (hi - lo) * k], flags=flags)
-            kev1[i].record()
-            dist.all_gather_into_tensor(counts_all, counts_local)
-            if rank == 0:
-                D.expand(padded, k, counts_all[:E], mode=0, row_lo=0, row_hi=n, out=out)
+        step()
         ev1[i].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     step_ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in zip(ev0, ev1)], dtype=torch.float64, device=dev)
     if world > 1:
-        kern_ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in zip(kev0, kev1)], dtype=torch.float64, device=dev)
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # max over ranks, per step
-        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+        # the dominant kernel alone (count kernel over this rank's slab), for the roofline record
+        nl = pg.launches
+        kt = []
+        if hi > lo:
+            for _ in range(3):
+                D.jaccard_counts(padded, n, k, lo, hi, out=counts_all[lo * k:hi * k], flags=flags)
+            for i in range(5):
+                flush.fill_(i)
+                kev0[0].record()
+                D.jaccard_counts(padded, n, k, lo, hi, out=counts_all[lo * k:hi * k], flags=flags)
+                kev1[0].record()
+                torch.cuda.synchronize()
+                kt.append(kev0[0].elapsed_time(kev1[0]))
+        kern_t = torch.tensor([sum(kt) / len(kt) if kt else 0.0, float(hi - lo), float(nl)], dtype=torch.float64, device=dev)
+        allk = [torch.zeros_like(kern_t) for _ in range(world)]
+        dist.all_gather(allk, kern_t)
+        slowest = max(allk, key=lambda v: float(v[0]))
+        kern_ms = slowest[:1]
+        kern_rows = int(slowest[1])
+        total_launches = int(sum(float(v[2]) for v in allk))
     else:
         kern_ms = step_ms
     assert int(flags[0]) == 0, "fast kernel flagged the synthetic input"
@@ -285,7 +324,7 @@ def run_ours(a):
     ms_per_step = total_ms / a.steps
     value = E / (ms_per_step * 1e-3)
     kern_avg_ms = float(kern_ms.mean())
-    edges_per_launch = E if world == 1 else sharding.slab_rows(n, world) * k
+    edges_per_launch = E if world == 1 else kern_rows * k
     bpe = bytes_per_edge if world == 1 else (4 * k + 4 + 1)  # count kernel writes 1 B/edge
     achieved = edges_per_launch * bpe / (kern_avg_ms * 1e-3) / 1e9
 
@@ -377,14 +416,21 @@ def run_ours(a):
                        "l2": "explicit 256 MiB flush write between timed steps; index 4*n*32 B = %.0f MB > 126 MB L2"
                              % (n * 32 * 4 / 1e6),
                        "sharding": "none" if world == 1 else
-                       "rows/%d; resident replicated int32 index; u8 count all-gather; expand on rank 0" % world,
+                       "rows over %d ranks, host rank takes %.1f%% (expand/count cost ratio %.3f measured); resident "
+                       "replicated int32 index; 4 chunks per rank; u8 counts reach rank 0 %s; expand kernel on rank 0 "
+                       "overlapping the next chunk" % (
+                           world, 100.0 * (pg.bounds[0][1] - pg.bounds[0][0]) / n, rho,
+                           "by peer stores from the count kernel's epilogue (CUDA IPC mapping over NVLink, flag per "
+                           "chunk)" if a.gather == "peer" else "over NCCL send/recv as counted"),
                        "launch": {"grid": g.value, "block": b.value, "smem": s.value}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None,
-                         "kernel": "jaccard_small_k_kernel<32,false>" if world == 1 and k <= 32 and k > 16 else "jaccard kernel",
+                         "kernel": ("jaccard_small_k_kernel<%d,%s>" % (D.row_stride(k), "false" if world == 1 else "true")) if k <= 32
+                         else ("jaccard_wide_k_kernel<%s>" % ("false" if world == 1 else "true")),
                          "bytes_per_edge": bpe, "edges_per_launch": edges_per_launch,
                          "kernel_ms": kern_avg_ms, "peak_source": peak_src},
-            "clocks": clocks, "gpu_launches": launches_per_step * a.steps,
+            "clocks": clocks,
+            "gpu_launches": launches_per_step * a.steps if world == 1 else int(total_launches * a.steps / (a.steps + max(3, a.warmup))),
             "loop_wall_ms": t_wall * 1e3,
         }
         if e2e:
@@ -393,6 +439,8 @@ def run_ours(a):
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
+        if a.gather == "peer":
+            pg.close()
         dist.destroy_process_group()
 
 
@@ -404,10 +452,16 @@ def C_int32():
 
 def main():
     a = parse()
+    # exactly ONE JSON line on stdout: libraries (NCCL's version banner ...) write to fd 1 too, so
+    # everything else goes to stderr and only the record is written to the real stdout
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
     if a.impl == "reference":
         run_reference_arm(a)
     else:
         run_ours(a)
+    real.flush()
 
 
 if __name__ == "__main__":

@@ -32,6 +32,14 @@ PROTOTYPES = {
     "gficf_cuda_comm_init_rank": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_size_t]),
     "gficf_cuda_comm_destroy": (C.c_int, []),
     "gficf_cuda_jaccard_rank": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_char_p, C.c_size_t]),
+    "gficf_cuda_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp), _vp]),
+    "gficf_cuda_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "gficf_cuda_ipc_close": (C.c_int, [_vp]),
+    "gficf_cuda_ipc_free": (C.c_int, [_vp]),
+    "gficf_cuda_signal_dev": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "gficf_cuda_wait_dev": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
+    "gficf_cuda_expand_wait_dev": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp,
+                                             C.c_uint32, _vp, _vp]),
     "gficf_cuda_row_stride": (C.c_int32, [C.c_int32]),
     "gficf_cuda_layout_dev": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
                                         C.c_int64, _vp, _vp, _vp]),

@@ -225,7 +225,8 @@ void launch_expand_t(const int* idx, int k, long long lo, long long hi, const CT
   const long long total = (hi - lo) * (long long)k;
   if (total <= 0) return;
   if (mode == GFICF_MODE_PARALLEL) {
-    expand_fixed_kernel<CT><<<grid_1d(total, 256, 8), 256, 0, st>>>(idx, k, kp, lo, hi, d_u, f, t, w);
+    expand_fixed_kernel<CT><<<grid_1d(total, kExpandThreads, 8), kExpandThreads, 0, st>>>(
+        idx, k, kp, lo, hi, d_u, f, t, w, nullptr, 0u, nullptr);
   } else {
     long long* chunk = (long long*)scratch;
     const long long nchunks = (total + kCompactChunk - 1) / kCompactChunk;
@@ -909,6 +910,96 @@ int gficf_cuda_jaccard_rank(const double* idx, int64_t n, int32_t k, double* out
                   std::chrono::duration<double, std::milli>(t1 - t0).count(), res.ms_gather,
                   (double)res.launches, 0};
   memcpy(tl_timings, tm, sizeof tm);
+  return GFICF_OK;
+  API_END
+}
+
+// ---------------------------------------------------------------- peer-memory gather
+int gficf_cuda_ipc_alloc(size_t bytes, void** dptr, void* handle64) {
+  char* err = nullptr;
+  size_t errlen = 0;
+  API_BEGIN
+  if (!dptr || !handle64 || !bytes) return GFICF_E_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == GFICF_IPC_HANDLE_BYTES, "ipc handle size");
+  void* p = nullptr;
+  CU_TRY(cudaMalloc(&p, bytes));
+  CU_TRY(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    CU_TRY(e);
+  }
+  memcpy(handle64, &h, sizeof h);
+  *dptr = p;
+  return GFICF_OK;
+  API_END
+}
+
+int gficf_cuda_ipc_open(const void* handle64, void** dptr) {
+  char* err = nullptr;
+  size_t errlen = 0;
+  API_BEGIN
+  if (!dptr || !handle64) return GFICF_E_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof h);
+  CU_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return GFICF_OK;
+  API_END
+}
+
+int gficf_cuda_ipc_close(void* dptr) {
+  if (dptr && cudaIpcCloseMemHandle(dptr) != cudaSuccess) {
+    cudaGetLastError();
+    return GFICF_E_CUDA;
+  }
+  return GFICF_OK;
+}
+
+int gficf_cuda_ipc_free(void* dptr) {
+  if (dptr && cudaFree(dptr) != cudaSuccess) {
+    cudaGetLastError();
+    return GFICF_E_CUDA;
+  }
+  return GFICF_OK;
+}
+
+int gficf_cuda_signal_dev(uint32_t* d_flag, uint32_t value, void* stream) {
+  char* err = nullptr;
+  size_t errlen = 0;
+  API_BEGIN
+  if (!d_flag) return GFICF_E_ARG;
+  signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_flag, value);
+  CU_TRY(cudaGetLastError());
+  return GFICF_OK;
+  API_END
+}
+
+int gficf_cuda_wait_dev(const uint32_t* d_flag, uint32_t expected, uint32_t* d_flags, void* stream) {
+  char* err = nullptr;
+  size_t errlen = 0;
+  API_BEGIN
+  if (!d_flag || !d_flags) return GFICF_E_ARG;
+  wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_flag, expected, d_flags);
+  CU_TRY(cudaGetLastError());
+  return GFICF_OK;
+  API_END
+}
+
+int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, int64_t row_hi,
+                               const uint8_t* d_u, double* d_from, double* d_to, double* d_w,
+                               const uint32_t* d_ready, uint32_t expected, uint32_t* d_flags,
+                               void* stream) {
+  char* err = nullptr;
+  size_t errlen = 0;
+  API_BEGIN
+  if (!d_idx_i32 || !d_u || !d_from || !d_to || !d_w || k < 1 || k > 255 || row_lo < 0) return GFICF_E_ARG;
+  if (d_ready && !d_flags) return GFICF_E_ARG;
+  const long long total = (row_hi - row_lo) * (long long)k;
+  if (total <= 0) return GFICF_OK;
+  expand_fixed_kernel<uint8_t><<<grid_1d(total, kExpandThreads, 8), kExpandThreads, 0, (cudaStream_t)stream>>>(
+      d_idx_i32, k, row_stride(k), row_lo, row_hi, d_u, d_from, d_to, d_w, d_ready, expected, d_flags);
+  CU_TRY(cudaGetLastError());
   return GFICF_OK;
   API_END
 }

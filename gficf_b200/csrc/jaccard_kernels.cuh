@@ -306,6 +306,7 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     }
     __syncwarp();
   }
+  if (COUNTS_ONLY) __threadfence_system();  // the counts may live in a peer GPU's memory
   if (warp_flags && lane == 0) atomicOr(flags, warp_flags);
 }
 
@@ -503,6 +504,7 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
     }
     __syncthreads();
   }
+  if (COUNTS_ONLY) __threadfence_system();  // the counts may live in a peer GPU's memory
   if (warp_flags && lane == 0) atomicOr(flags, warp_flags);
 }
 
@@ -539,23 +541,84 @@ jaccard_exact_kernel(const int* __restrict__ idx, int k, int kp, long long row_l
 // ---------------------------------------------------------------------------
 // counts -> edge rows, fixed slots (mode 0).  One thread per edge, streaming.
 // ---------------------------------------------------------------------------
+// When `ready` is given, every CTA first waits until *ready >= expected: the counts of this row
+// range are being stored into this GPU's memory by a PEER GPU's count kernel (NVLink stores), and
+// the peer raises the flag (signal_kernel) once that kernel has finished.  A bounded spin: after
+// ~2^31 clocks the kernel gives up and reports GFICF_FLAG_PEER_TIMEOUT instead of hanging the GPU.
+constexpr unsigned kFlagPeerTimeout = 8u;
+
+constexpr int kExpandThreads = 256;
+
 template <typename CT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kExpandThreads)
 expand_fixed_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo, long long row_hi,
-                    const CT* __restrict__ d_u, double* __restrict__ o_from,
-                    double* __restrict__ o_to, double* __restrict__ o_w) {
-  const long long total = (row_hi - row_lo) * (long long)k;
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total;
-       r += (long long)gridDim.x * blockDim.x) {
-    const long long rr = r / k;
-    const int j = (int)(r - rr * k);
-    const int u = (int)d_u[r];
-    const bool nz = u > 0;
-    const int t = nz ? __ldg(idx + (row_lo + rr) * (long long)kp + j) : 0;
-    __stcs(o_from + r, nz ? (double)(row_lo + rr + 1) : 0.0);
-    __stcs(o_to + r, nz ? (double)(t + 1) : 0.0);
-    __stcs(o_w + r, nz ? jaccard_weight(u, k) : 0.0);
+                    const CT* d_u, double* __restrict__ o_from, double* __restrict__ o_to,
+                    double* __restrict__ o_w, const volatile unsigned* ready, unsigned expected,
+                    unsigned* flags) {
+  __shared__ double lut[256];
+  const bool use_lut = k <= 255;
+  if (use_lut && (int)threadIdx.x <= k) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
+  if (ready != nullptr && threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while ((int)(*ready - expected) < 0) {
+      if (clock64() - t0 > (1ll << 31)) {
+        atomicOr(flags, kFlagPeerTimeout);
+        break;
+      }
+      __nanosleep(200);
+    }
+    __threadfence();
   }
+  __syncthreads();
+  // Grid-stride over the edges (at any moment the whole grid writes ONE contiguous window of each
+  // output array: DRAM-page friendly), with a (row, j) walk that needs no division per edge:
+  // one division per thread, then fixed increments.
+  const long long total = (row_hi - row_lo) * (long long)k;
+  const long long stride = (long long)gridDim.x * kExpandThreads;
+  const long long g0 = (long long)blockIdx.x * kExpandThreads + threadIdx.x;
+  long long row = row_lo + g0 / k;
+  int j = (int)(g0 % k);
+  const long long d_row = stride / k;
+  const int d_j = (int)(stride % k);
+#pragma unroll 4
+  for (long long e = g0; e < total; e += stride) {
+    // the counts may have been stored by a peer GPU: read them from L2 (ld.global.cg), the point
+    // of coherence for this GPU's memory, never through the non-coherent path
+    const int u = (int)__ldcg(d_u + e);
+    // the id is loaded unconditionally: a load that waits for u first doubles the latency chain
+    // (measured 0.98 -> 0.62 ms at 4M x 30, tools/expand_bench.cu)
+    const int t = __ldg(idx + row * (long long)kp + j);
+    const bool nz = u > 0;
+    __stcs(o_from + e, nz ? (double)(row + 1) : 0.0);
+    __stcs(o_to + e, nz ? (double)(t + 1) : 0.0);
+    __stcs(o_w + e, use_lut ? lut[u] : (nz ? jaccard_weight(u, k) : 0.0));
+    row += d_row;
+    j += d_j;
+    if (j >= k) {
+      j -= k;
+      ++row;
+    }
+  }
+}
+
+// holds the stream until *flag >= expected (bounded spin, see expand_fixed_kernel)
+__global__ void wait_kernel(const volatile unsigned* flag, unsigned expected, unsigned* flags) {
+  const long long t0 = clock64();
+  while ((int)(*flag - expected) < 0) {
+    if (clock64() - t0 > (1ll << 31)) {
+      atomicOr(flags, kFlagPeerTimeout);
+      break;
+    }
+    __nanosleep(500);
+  }
+  __threadfence_system();
+}
+
+// raises a (possibly peer-resident) flag once everything before it in the stream has finished
+__global__ void signal_kernel(unsigned* flag, unsigned value) {
+  __threadfence_system();
+  *(volatile unsigned*)flag = value;
+  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------

@@ -129,10 +129,65 @@ def expand(idx_i32: torch.Tensor, k: int, counts: torch.Tensor, mode: int = 0, r
     if out is None:
         out = torch.empty((3, e), dtype=torch.float64, device=dev)
     L = _lib.lib()
-    scratch = torch.empty((max(int(L.gficf_cuda_expand_scratch_bytes(e)), 8),), dtype=torch.uint8, device=dev)
-    nw = torch.zeros(1, dtype=torch.int64, device=dev)
+    scratch_ptr, nw, nw_ptr = 0, None, 0
+    if mode == 1:
+        scratch = torch.empty((max(int(L.gficf_cuda_expand_scratch_bytes(e)), 8),), dtype=torch.uint8, device=dev)
+        nw = torch.zeros(1, dtype=torch.int64, device=dev)
+        scratch_ptr, nw_ptr = scratch.data_ptr(), nw.data_ptr()
     with torch.cuda.device(dev):
         _lib.check(L.gficf_cuda_expand_dev(idx_i32.data_ptr(), k, row_lo, hi, counts.data_ptr(), mode,
                                            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
-                                           scratch.data_ptr(), nw.data_ptr(), _stream_ptr()))
+                                           scratch_ptr, nw_ptr, _stream_ptr()))
     return out, nw
+
+
+# ---- raw-pointer variants for the peer-memory gather (buffers allocated / mapped by the library)
+def ipc_alloc(nbytes: int):
+    """cudaMalloc'ed, zeroed, exportable buffer on the current device -> (ptr, 64-byte handle)."""
+    p = C.c_void_p()
+    h = C.create_string_buffer(64)
+    _lib.check(_lib.lib().gficf_cuda_ipc_alloc(nbytes, C.byref(p), h))
+    return int(p.value), h.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    p = C.c_void_p()
+    _lib.check(_lib.lib().gficf_cuda_ipc_open(C.create_string_buffer(handle, 64), C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(ptr: int) -> None:
+    _lib.lib().gficf_cuda_ipc_close(ptr)
+
+
+def ipc_free(ptr: int) -> None:
+    _lib.lib().gficf_cuda_ipc_free(ptr)
+
+
+def jaccard_counts_to(idx_i32: torch.Tensor, n: int, k: int, row_lo: int, row_hi: int, out_ptr: int,
+                      flags: torch.Tensor) -> None:
+    """Count kernel writing its u8 results at the raw device address out_ptr (may be peer memory)."""
+    _require_cuda(idx_i32, torch.int32)
+    with torch.cuda.device(idx_i32.device):
+        _lib.check(_lib.lib().gficf_cuda_jaccard_counts_dev(idx_i32.data_ptr(), n, k, row_lo, row_hi, out_ptr,
+                                                            flags.data_ptr(), _stream_ptr()))
+
+
+def signal(flag_ptr: int, value: int) -> None:
+    _lib.check(_lib.lib().gficf_cuda_signal_dev(flag_ptr, value & 0xFFFFFFFF, _stream_ptr()))
+
+
+def wait_flag(flag_ptr: int, expected: int, flags: torch.Tensor) -> None:
+    _lib.check(_lib.lib().gficf_cuda_wait_dev(flag_ptr, expected & 0xFFFFFFFF, flags.data_ptr(), _stream_ptr()))
+
+
+def expand_wait(idx_i32: torch.Tensor, k: int, row_lo: int, row_hi: int, counts_ptr: int, out3: torch.Tensor,
+                ready_ptr: int, expected: int, flags: torch.Tensor) -> None:
+    """Fixed-slot expand of rows [row_lo,row_hi) from counts at counts_ptr (slab-relative) into
+    out3[:, row_lo*k:row_hi*k], after *ready_ptr >= expected (ready_ptr = 0: no wait)."""
+    sl = out3[:, row_lo * k:row_hi * k]
+    with torch.cuda.device(idx_i32.device):
+        _lib.check(_lib.lib().gficf_cuda_expand_wait_dev(idx_i32.data_ptr(), k, row_lo, row_hi, counts_ptr,
+                                                         sl[0].data_ptr(), sl[1].data_ptr(), sl[2].data_ptr(),
+                                                         ready_ptr or None, expected & 0xFFFFFFFF,
+                                                         flags.data_ptr(), _stream_ptr()))

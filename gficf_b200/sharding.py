@@ -150,3 +150,182 @@ def rcpp_parallel_jaccard_coef_sharded(mat, n: int, k: int, out=None, group=None
     torch.from_numpy(out.T).copy_(res, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Pipelined gather to the host rank.
+#
+# With the final (E x 3) f64 matrix required in ONE GPU's HBM, the host rank must write 24 B per
+# edge of the WHOLE matrix (the expand kernel) while the other ranks only count.  So the rows are
+# split unevenly -- the host rank counts fewer rows (none from ~6 ranks on) -- and each rank's slab
+# is cut into chunks that are sent (1 byte per edge, NCCL send/recv over NVLink) as soon as they
+# are counted, so that the host rank's expansion of chunk c overlaps everybody's counting of
+# chunk c+1.
+# ---------------------------------------------------------------------------------------------
+def weighted_bounds(n: int, world: int, rho: float, host_rank: int = 0):
+    """Row ranges per rank.  rho = (time to expand a row) / (time to count a row) on one GPU.
+    Balancing  x*Tc + Te = (1-x)*Tc/(world-1)  gives the host rank's share x = (1 - rho*(world-1))/world."""
+    if world == 1:
+        return [(0, n)]
+    x = max(0.0, (1.0 - rho * (world - 1)) / world)
+    rows0 = int(round(x * n))
+    rest = n - rows0
+    per = (rest + world - 2) // (world - 1)
+    out, lo = [], 0
+    others = 0
+    for r in range(world):
+        if r == host_rank:
+            out.append((lo, lo + rows0))
+            lo += rows0
+        else:
+            hi = min(n, lo + per) if others < world - 2 else n
+            out.append((lo, hi))
+            lo = hi
+            others += 1
+    assert lo == n
+    return out
+
+
+def chunk_bounds(lo: int, hi: int, chunks: int):
+    per = (hi - lo + chunks - 1) // chunks if hi > lo else 0
+    return [(min(hi, lo + c * per), min(hi, lo + (c + 1) * per)) for c in range(chunks)]
+
+
+class PipelinedGather:
+    """Counts on every rank, chunked sends to the host rank, expansion there.
+
+    compute_counts(idx, n, k, lo, hi, out_u8_view) and expand(idx, k, counts_view, lo, hi, out3)
+    default to the library kernels; tests inject stand-ins to run the same schedule over gloo."""
+
+    def __init__(self, n: int, k: int, group=None, rho: float = 0.2, chunks: int = 4, host_rank: int = 0,
+                 compute_counts=None, expand=None):
+        self.n, self.k, self.group, self.host = n, k, group, host_rank
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.bounds = weighted_bounds(n, self.world, rho, host_rank)
+        self.chunks = [chunk_bounds(lo, hi, chunks) for lo, hi in self.bounds]
+        self.compute_counts = compute_counts or self._lib_counts
+        self.expand = expand or self._lib_expand
+        self.flags = None
+        self.launches = 0  # kernels this rank launched (count + expand), for the bench record
+
+    def _lib_counts(self, idx, n, k, lo, hi, out):
+        from . import device as D
+
+        if self.flags is None:
+            self.flags = D.new_flags(idx.device)
+        D.jaccard_counts(idx, n, k, lo, hi, out=out, flags=self.flags)
+        self.launches += 1
+
+    def _lib_expand(self, idx, k, counts, lo, hi, out3):
+        from . import device as D
+
+        # out3 is [3, E]; the kernel writes slab-relative, so hand it the slab's columns
+        D.expand(idx, k, counts, mode=0, row_lo=lo, row_hi=hi, out=out3[:, lo * k:hi * k])
+        self.launches += 1
+
+    def step(self, idx_full, counts_all, out3):
+        """counts_all: uint8 [n*k] on every rank (only the own rows are used off the host rank);
+        out3: float64 [3, n*k] on the host rank (None elsewhere)."""
+        k, n = self.k, self.n
+        if self.rank != self.host:
+            works = []
+            for lo, hi in self.chunks[self.rank]:
+                if hi > lo:
+                    view = counts_all[lo * k:hi * k]
+                    self.compute_counts(idx_full, n, k, lo, hi, view)
+                    works += dist.batch_isend_irecv([dist.P2POp(dist.isend, view, self.host, self.group)])
+            for w in works:
+                w.wait()
+            return
+        recvs = {}
+        nchunks = len(self.chunks[0])
+        for c in range(nchunks):  # post every receive first; they complete as the chunks arrive
+            for r in range(self.world):
+                lo, hi = self.chunks[r][c]
+                if r != self.host and hi > lo:
+                    recvs[(r, c)] = dist.batch_isend_irecv(
+                        [dist.P2POp(dist.irecv, counts_all[lo * k:hi * k], r, self.group)])[0]
+        for c in range(nchunks):
+            lo, hi = self.chunks[self.host][c]
+            if hi > lo:
+                self.compute_counts(idx_full, n, k, lo, hi, counts_all[lo * k:hi * k])
+                self.expand(idx_full, k, counts_all[lo * k:hi * k], lo, hi, out3)
+            for r in range(self.world):
+                if (r, c) in recvs:
+                    recvs[(r, c)].wait()
+                    lo, hi = self.chunks[r][c]
+                    self.expand(idx_full, k, counts_all[lo * k:hi * k], lo, hi, out3)
+
+
+class PeerGather:
+    """The same schedule as PipelinedGather with the gather FUSED into the count kernel: the host
+    rank exports its count buffer (CUDA IPC), the other ranks map it and their count kernels store
+    the 1-byte results straight into the host rank's HBM over NVLink; a flag per rank (raised by a
+    one-thread kernel behind each chunk) tells the host rank's expand kernel that a chunk has
+    landed.  No collective kernel competes for SMs with the persistent count kernels.
+
+    torch.distributed only carries the 64-byte IPC handle at construction."""
+
+    def __init__(self, n: int, k: int, group=None, rho: float = 0.2, chunks: int = 4, host_rank: int = 0):
+        from . import device as D
+
+        self.D = D
+        self.n, self.k, self.group, self.host = n, k, group, host_rank
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.bounds = weighted_bounds(n, self.world, rho, host_rank)
+        self.chunks = [chunk_bounds(lo, hi, chunks) for lo, hi in self.bounds]
+        self.nchunks = chunks
+        self.epoch = 0
+        self.launches = 0
+        e = n * k
+        self.flag_off = (e + 255) // 256 * 256          # [world] chunk flags, then the ack flag
+        nbytes = self.flag_off + 4 * (self.world + 1)
+        box = [None]
+        if self.rank == host_rank:
+            self.base, handle = D.ipc_alloc(nbytes)
+            box = [handle]
+        dist.broadcast_object_list(box, src=host_rank, group=group)
+        if self.rank != host_rank:
+            self.base = D.ipc_open(box[0])
+        self.flags = D.new_flags(torch.device("cuda", torch.cuda.current_device()))
+        dist.barrier(group=group)
+
+    def _flag(self, r):
+        return self.base + self.flag_off + 4 * r
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        if self.rank == self.host:
+            self.D.ipc_free(self.base)
+        else:
+            self.D.ipc_close(self.base)
+
+    def step(self, idx_full, out3):
+        D, k, n, C_ = self.D, self.k, self.n, self.nchunks
+        base_val = self.epoch * C_
+        ack = self._flag(self.world)
+        if self.rank != self.host:
+            # the host rank must have consumed the previous step's counts before they are overwritten
+            D.wait_flag(ack, self.epoch, self.flags)
+            for c, (lo, hi) in enumerate(self.chunks[self.rank]):
+                if hi > lo:
+                    D.jaccard_counts_to(idx_full, n, k, lo, hi, self.base + lo * k, self.flags)
+                    self.launches += 1
+                D.signal(self._flag(self.rank), base_val + c + 1)
+            self.epoch += 1
+            return
+        for c in range(C_):
+            lo, hi = self.chunks[self.host][c]
+            if hi > lo:
+                D.jaccard_counts_to(idx_full, n, k, lo, hi, self.base + lo * k, self.flags)
+                D.expand_wait(idx_full, k, lo, hi, self.base + lo * k, out3, 0, 0, self.flags)
+                self.launches += 2
+            for r in range(self.world):
+                lo, hi = self.chunks[r][c]
+                if r != self.host and hi > lo:
+                    D.expand_wait(idx_full, k, lo, hi, self.base + lo * k, out3, self._flag(r), base_val + c + 1,
+                                  self.flags)
+                    self.launches += 1
+        self.epoch += 1
+        D.signal(ack, self.epoch)

@@ -130,6 +130,28 @@ int gficf_cuda_jaccard_rank(const double* idx_colmajor, int64_t n, int32_t k, do
                             char* err, size_t errlen);
 
 /* ======================================================================== *
+ *  Peer-memory gather (fused compute + gather over NVLink, one process per GPU):
+ *  the host rank allocates the count buffer and exports it; the other ranks map
+ *  it and pass the mapped pointer as d_u of gficf_cuda_jaccard_counts_dev, so the
+ *  count kernel's epilogue stores its 1-byte results straight into the host
+ *  rank's HBM.  gficf_cuda_signal_dev raises a flag in that buffer when the
+ *  stream reaches it; gficf_cuda_expand_wait_dev is the expand kernel that first
+ *  waits for the flag (bounded spin; GFICF_FLAG_PEER_TIMEOUT on give-up).
+ * ======================================================================== */
+#define GFICF_IPC_HANDLE_BYTES 64
+#define GFICF_FLAG_PEER_TIMEOUT 8u
+int gficf_cuda_ipc_alloc(size_t bytes, void** dptr, void* handle64); /* cudaMalloc + zero + export */
+int gficf_cuda_ipc_open(const void* handle64, void** dptr);          /* map a peer's allocation   */
+int gficf_cuda_ipc_close(void* dptr);
+int gficf_cuda_ipc_free(void* dptr);
+int gficf_cuda_signal_dev(uint32_t* d_flag, uint32_t value, void* stream);
+int gficf_cuda_wait_dev(const uint32_t* d_flag, uint32_t expected, uint32_t* d_flags, void* stream);
+int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, int64_t row_hi,
+                               const uint8_t* d_u, double* d_from, double* d_to, double* d_w,
+                               const uint32_t* d_ready, uint32_t expected, uint32_t* d_flags,
+                               void* stream);
+
+/* ======================================================================== *
  *  Device-buffer entry points (resident data: the benchmarked kernels, and
  *  the building blocks a multi-process (one rank per GPU) caller shards with)
  *  All pointers are device pointers on the CURRENT device; `stream` is a

@@ -75,6 +75,33 @@ for n, k, dup in ((200_000, 30, False), (10_001, 15, False), (5_000, 100, False)
         assert np.array_equal(out, want), (n, k)
     else:
         assert out is None
+# pipelined gather: uneven split, chunked u8 sends, expand on the host rank
+from gficf_b200 import device as D
+for n, k, rho in ((300_000, 30, 0.19), (50_001, 15, 0.6), (20_000, 100, 0.0)):
+    idx0 = synth.knn_index(n, k, scramble=True, device="cuda")
+    padded, fl = D.pad_rows(idx0)
+    pg = sharding.PipelinedGather(n, k, rho=rho, chunks=4)
+    counts = torch.empty(n * k, dtype=torch.uint8, device="cuda")
+    out3 = torch.full((3, n * k), -1.0, dtype=torch.float64, device="cuda") if rank == 0 else None
+    pg.step(padded, counts, out3)
+    pg.step(padded, counts, out3)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref, _ = D.jaccard_edges(padded, n, k)
+        assert torch.equal(out3, ref), (n, k)
+        assert int(pg.flags[0]) == 0
+    dist.barrier()
+    # the same schedule with the gather fused into the count kernel (peer stores over NVLink)
+    peer = sharding.PeerGather(n, k, rho=rho, chunks=4)
+    if rank == 0:
+        out3.fill_(-1.0)
+    for it in range(3):
+        peer.step(padded, out3)
+    torch.cuda.synchronize()
+    if rank == 0:
+        assert torch.equal(out3, ref), ("peer", n, k)
+    assert int(peer.flags[0]) == 0
+    peer.close()
 # the library's own one-rank-per-GPU entry on shared page-locked host matrices
 from gficf_b200 import multiproc
 multiproc.comm_init_from_torch()

@@ -79,3 +79,71 @@ def test_slab_bounds_cover_rows_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert all(hi - lo <= sharding.slab_rows(n, world) for lo, hi in spans)
+
+
+def _pipe_worker(rank, world, port, n, k, rho, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.binding import Oracle
+
+        orc = Oracle()
+        idx = synth.knn_index(n, k, seed=3)
+        r = synth.to_r_matrix(idx)
+        lut = np.array([u / (2.0 * k - u) for u in range(k + 1)])
+
+        def compute(idx_, n_, k_, lo, hi, out):
+            w = orc.parallel_rows(r, lo, hi, nthreads=1)[:, 2]
+            out.copy_(torch.from_numpy(np.searchsorted(lut, w).astype(np.uint8)))
+
+        def expand(idx_, k_, counts, lo, hi, out3):
+            u = counts.numpy().astype(np.int64)
+            rows = np.repeat(np.arange(lo, hi), k_) + 1.0
+            nz = u > 0
+            out3[0, lo * k_:hi * k_] = torch.from_numpy(np.where(nz, rows, 0.0))
+            out3[1, lo * k_:hi * k_] = torch.from_numpy(np.where(nz, idx_[lo:hi].numpy().reshape(-1) + 1.0, 0.0))
+            out3[2, lo * k_:hi * k_] = torch.from_numpy(lut[u])
+
+        pg = sharding.PipelinedGather(n, k, rho=rho, chunks=3, compute_counts=compute, expand=expand)
+        counts = torch.zeros(n * k, dtype=torch.uint8)
+        out3 = torch.full((3, n * k), -1.0, dtype=torch.float64) if rank == 0 else None
+        pg.step(idx, counts, out3)
+        pg.step(idx, counts, out3)  # the schedule is re-entrant
+        q.put((rank, pg.bounds, out3.numpy().copy() if rank == 0 else None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,rho", [(2, 0.2), (3, 0.6), (2, 0.0)])
+def test_pipelined_gather_schedule(oracle, world, rho):
+    """Uneven row split + chunked send/recv + host-rank expansion reproduce the whole matrix."""
+    n, k = 999, 15
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipe_worker, args=(r, world, port, n, k, rho, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = oracle.parallel(synth.to_r_matrix(synth.knn_index(n, k, seed=3)))
+    for rank, bounds, out in got:
+        assert bounds[0][0] == 0 and bounds[-1][1] == n and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+        if rank == 0:
+            assert np.array_equal(out.T, want)
+    if rho >= 0.5 and world == 3:
+        assert got[0][1][0] == (0, 0)  # the host rank only expands
+
+
+def test_weighted_bounds():
+    for n in (10, 1000, 4_000_000):
+        for world in (1, 2, 4, 8):
+            for rho in (0.0, 0.19, 0.5, 2.0):
+                b = sharding.weighted_bounds(n, world, rho)
+                assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+                assert all(x[1] == y[0] for x, y in zip(b, b[1:])) and all(hi >= lo for lo, hi in b)
+    # rho = 0: an even split
+    assert [hi - lo for lo, hi in sharding.weighted_bounds(1000, 4, 0.0)] == [250, 250, 250, 250]
