@@ -99,8 +99,16 @@ int32_t row_stride(int32_t k) {
   return (k + 7) / 8 * 8;
 }
 
-// table slots ~ k^2/2: a multiplier is collision free with probability >= ~0.37
-int wide_log_ts(int k) { return k <= 45 ? 10 : (k <= 64 ? 11 : (k <= 90 ? 12 : 13)); }
+// Table slots per warp-group.  A multiplier is collision free with probability ~exp(-k^2/2/slots)
+// (0.37 at slots = k^2/2, 0.14 at k=128 in 4096 slots); a failed try costs warp 0 ~150 cycles of a
+// ~20k-cycle row, so the smaller table (more resident warp-groups) wins.
+#ifndef GFICF_WIDE_MAX_LOG_TS
+#define GFICF_WIDE_MAX_LOG_TS 12
+#endif
+int wide_log_ts(int k) {
+  const int want = k <= 45 ? 10 : (k <= 64 ? 11 : (k <= 90 ? 12 : 13));
+  return want < GFICF_WIDE_MAX_LOG_TS ? want : GFICF_WIDE_MAX_LOG_TS;
+}
 
 size_t wide_smem_bytes(int log_ts) { return (size_t)wide_smem_words(log_ts) * 4 + 129 * sizeof(double); }
 

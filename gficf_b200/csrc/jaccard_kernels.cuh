@@ -33,6 +33,12 @@
 #ifndef GFICF_SMALL_LOG_TS32
 #define GFICF_SMALL_LOG_TS32 9   // hash-table slots per warp for 16 < k <= 32: 2^9
 #endif
+#ifndef GFICF_SMALL_WARPS
+#define GFICF_SMALL_WARPS 7      // warps (rows in flight) per CTA of the k<=32 kernel
+#endif
+#ifndef GFICF_WIDE_MINB
+#define GFICF_WIDE_MINB 8        // resident CTAs (warp-groups) per SM the 32<k<=128 kernel is compiled for
+#endif
 #ifndef GFICF_SMALL_MINB
 #define GFICF_SMALL_MINB 4       // resident CTAs per SM the k<=32 kernel is compiled for
 #endif
@@ -196,7 +202,7 @@ struct SmallK {
   static constexpr int TS = 1 << LOG_TS;
 };
 
-constexpr int kSmallWarps = 8;
+constexpr int kSmallWarps = GFICF_SMALL_WARPS;
 
 template <int KP, bool COUNTS_ONLY>
 __global__ void __launch_bounds__(kSmallWarps * 32, GFICF_SMALL_MINB)
@@ -323,7 +329,8 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
 constexpr int kWideWarps = 4;
 constexpr int kWideU = 8;  // neighbour rows in flight per warp
 
-__host__ __device__ constexpr int wide_smem_words(int log_ts) { return (1 << log_ts) + 128 + 128 + 4; }
+// table | 2 x own-row ids | 2 x counts (double-buffered across rows) | multiplier
+__host__ __device__ constexpr int wide_smem_words(int log_ts) { return (1 << log_ts) + 256 + 256 + 4; }
 
 // N neighbour rows of one batch: issue the gathers / probe them.  N is a template
 // parameter (dispatched on the warp-uniform batch size) so that both are branch-free and the
@@ -364,7 +371,7 @@ __device__ __forceinline__ void wide_probe(const int4 (&v)[kWideU], unsigned tbl
   }
 
 template <int LOG_TS, bool COUNTS_ONLY>
-__global__ void __launch_bounds__(kWideWarps * 32)
+__global__ void __launch_bounds__(kWideWarps * 32, GFICF_WIDE_MINB)
 jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo,
                       long long row_hi, double* __restrict__ o_from, double* __restrict__ o_to,
                       double* __restrict__ o_w, uint8_t* __restrict__ o_u,
@@ -372,9 +379,9 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
   constexpr int TS = 1 << LOG_TS, SHIFT = 32 - LOG_TS;
   extern __shared__ unsigned smem_u[];
   unsigned* tbl = smem_u;                             // [TS]
-  int* srow = reinterpret_cast<int*>(tbl + TS);        // [128] ids of row i
-  int* scnt = srow + 128;                              // [128] u per edge
-  unsigned* s_mult = reinterpret_cast<unsigned*>(scnt + 128);  // [4]
+  int* srow_base = reinterpret_cast<int*>(tbl + TS);   // [2][128] ids of row i
+  int* scnt_base = srow_base + 256;                    // [2][128] u per edge
+  unsigned* s_mult = reinterpret_cast<unsigned*>(scnt_base + 256);  // [4]
   double* lut = reinterpret_cast<double*>(s_mult + 4);  // [129]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -399,7 +406,12 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
 
   int a_next = (row_lo + blockIdx.x < row_hi && tid < kp)
                    ? __ldg(idx + (row_lo + blockIdx.x) * (long long)kp + tid) : kPadId;
-  for (long long row = row_lo + blockIdx.x; row < row_hi; row += gridDim.x) {
+  int parity = 0;
+  for (long long row = row_lo + blockIdx.x; row < row_hi; row += gridDim.x, parity ^= 1) {
+    // srow / scnt alternate between two buffers, so the epilogue of row r may still read its
+    // buffers while the next row is being staged: 3 block barriers per row instead of 4
+    int* srow = srow_base + parity * 128;
+    int* scnt = scnt_base + parity * 128;
     srow[tid] = a_next;  // blockDim == 128 == capacity of srow
     {
       const long long nrow = row + gridDim.x;
@@ -502,7 +514,7 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
       }
       tbl[((unsigned)srow[tid] * mult) >> SHIFT] = kEmpty;  // leave the table empty
     }
-    __syncthreads();
+    // no barrier here: the next row's first barrier orders these erasures before warp 0 rebuilds
   }
   if (COUNTS_ONLY) __threadfence_system();  // the counts may live in a peer GPU's memory
   if (warp_flags && lane == 0) atomicOr(flags, warp_flags);

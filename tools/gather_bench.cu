@@ -1,0 +1,71 @@
+// Micro-benchmark: ceiling of a random 128-byte-row gather (+ 24 B/edge streaming write) on B200.
+// Same access pattern as jaccard_small_k_kernel at k=30 (8 lanes per row, 8 LDG.128 per lane in
+// flight, index read first), but no hashing / probing at all.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+#include <random>
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("%s: %s\n",#x,cudaGetErrorString(e)); return 1;}}while(0)
+
+template <int WARPS, bool WRITE>
+__global__ void __launch_bounds__(WARPS * 32) gather(const int* __restrict__ idx, long long n,
+    double* __restrict__ f, double* __restrict__ t_, double* __restrict__ w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nwarps = (long long)gridDim.x * WARPS;
+  const int sub4 = (lane & 7) * 4, grp = lane >> 3;
+  long long row = (long long)blockIdx.x * WARPS + warp;
+  int a_next = row < n ? __ldg(idx + row * 32 + lane) : 0;
+  for (; row < n; row += nwarps) {
+    const int a = a_next;
+    const long long nrow = row + nwarps;
+    a_next = nrow < n ? __ldg(idx + nrow * 32 + lane) : 0;
+    int4 v[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int t = __shfl_sync(0xffffffffu, a, grp * 8 + s);
+      v[s] = __ldg(reinterpret_cast<const int4*>(idx + (long long)t * 32 + sub4));
+    }
+    int acc = 0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) acc += v[s].x ^ v[s].y ^ v[s].z ^ v[s].w;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (WRITE) {
+      if (lane < 30) {
+        const long long r = row * 30 + lane;
+        __stcs(f + r, (double)(row + 1)); __stcs(t_ + r, (double)(a + 1)); __stcs(w + r, (double)acc);
+      }
+    } else if (acc == 0x7fffffff) f[0] = 1.0;
+  }
+}
+
+int main() {
+  const long long n = 4000000; const long long E = n * 30;
+  std::vector<int> h(n * 32);
+  std::mt19937_64 rng(1);
+  for (long long i = 0; i < n * 32; ++i) h[i] = (int)(rng() % n);
+  int* idx; double* out; uint8_t* flush;
+  CK(cudaMalloc(&idx, n * 32 * 4)); CK(cudaMalloc(&out, 3 * E * 8)); CK(cudaMalloc(&flush, 256 << 20));
+  CK(cudaMemcpy(idx, h.data(), n * 32 * 4, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int cfg = 0; cfg < 6; ++cfg) {
+    float tot = 0;
+    for (int it = 0; it < 6; ++it) {
+      CK(cudaMemset(flush, it, 256 << 20));
+      cudaEventRecord(e0);
+      switch (cfg) {
+        case 0: gather<8, true><<<148 * 4, 256>>>(idx, n, out, out + E, out + 2 * E); break;
+        case 1: gather<8, true><<<148 * 6, 256>>>(idx, n, out, out + E, out + 2 * E); break;
+        case 2: gather<8, true><<<148 * 8, 256>>>(idx, n, out, out + E, out + 2 * E); break;
+        case 3: gather<8, false><<<148 * 8, 256>>>(idx, n, out, out + E, out + 2 * E); break;
+        case 4: gather<8, true><<<148 * 3, 256>>>(idx, n, out, out + E, out + 2 * E); break;
+        case 5: gather<8, true><<<148 * 2, 256>>>(idx, n, out, out + E, out + 2 * E); break;
+      }
+      cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+      float ms; cudaEventElapsedTime(&ms, e0, e1); if (it) tot += ms;
+    }
+    const char* nm[] = {"4 CTA/SM write", "6 CTA/SM write", "8 CTA/SM write", "8 CTA/SM read-only", "3 CTA/SM write", "2 CTA/SM write"};
+    printf("%-20s %.3f ms  %.2f Gedges/s  %.0f GB/s algorithmic\n", nm[cfg], tot / 5, E / (tot / 5) / 1e6, E * 148.0 / (tot / 5) / 1e6);
+  }
+  return 0;
+}
