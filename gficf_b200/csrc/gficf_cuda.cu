@@ -96,7 +96,7 @@ int32_t row_stride(int32_t k) {
   if (k <= 8) return 8;
   if (k <= 16) return 16;
   if (k <= 32) return 32;
-  return (k + 7) / 8 * 8;
+  return (k + 15) / 16 * 16;  // 64-byte rows: a row never straddles an extra DRAM burst
 }
 
 // Table slots per warp-group.  A multiplier is collision free with probability ~exp(-k^2/2/slots)

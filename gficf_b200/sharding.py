@@ -227,6 +227,10 @@ class PipelinedGather:
         """counts_all: uint8 [n*k] on every rank (only the own rows are used off the host rank);
         out3: float64 [3, n*k] on the host rank (None elsewhere)."""
         k, n = self.k, self.n
+        if self.flags is None and idx_full.is_cuda:
+            from . import device as D
+
+            self.flags = D.new_flags(idx_full.device)
         if self.rank != self.host:
             works = []
             for lo, hi in self.chunks[self.rank]:

@@ -159,9 +159,9 @@ int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_
  * ======================================================================== */
 
 /* Row stride (in int32 elements) of the device index layout for a given k:
- * rows are padded so that every row starts on a 32-byte sector and is read
- * with 16-byte vector loads (k<=4:4, <=8:8, <=16:16, <=32:32, else k rounded
- * up to a multiple of 8).  Pad entries hold -2. */
+ * rows are padded so that every row is read with 16-byte vector loads and
+ * never straddles an extra 64-byte DRAM burst (k<=4:4, <=8:8, <=16:16, <=32:32,
+ * else k rounded up to a multiple of 16).  Pad entries hold -2. */
 int32_t gficf_cuda_row_stride(int32_t k);
 
 /* Layout pre-pass for rows [row_lo,row_hi): n x k f64 column-major 1-based

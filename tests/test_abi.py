@@ -32,7 +32,7 @@ def test_version_and_row_stride():
     L = gficf_b200.lib()
     assert b"sm_100a" in L.gficf_cuda_version()
     assert [L.gficf_cuda_row_stride(k) for k in (1, 4, 5, 8, 15, 16, 30, 32, 33, 100, 128)] == \
-        [4, 4, 8, 8, 16, 16, 32, 32, 40, 104, 128]
+        [4, 4, 8, 8, 16, 16, 32, 32, 48, 112, 128]
     assert L.gficf_cuda_expand_scratch_bytes(0) >= 8
 
 

@@ -149,5 +149,10 @@ def test_one_process_per_gpu_nccl(cuda, tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(nd, 4)),
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    log = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log):
+        with open(os.path.join(log, "worker_multi.log"), "w") as f:
+            f.write(out.stdout + "\n==== stderr ====\n" + out.stderr)
+    err_lines = [ln for ln in out.stderr.splitlines() if "Error" in ln or "assert" in ln.lower()]
+    assert out.returncode == 0, "\n".join(err_lines[-30:]) + out.stderr[-1500:]
     assert "SHARDED_OK" in out.stdout

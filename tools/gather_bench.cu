@@ -8,7 +8,20 @@
 #include <random>
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("%s: %s\n",#x,cudaGetErrorString(e)); return 1;}}while(0)
 
-template <int WARPS, bool WRITE>
+__device__ __forceinline__ int4 ld_na(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int4 ld_ef(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+template <int WARPS, bool WRITE, int LD = 0>
 __global__ void __launch_bounds__(WARPS * 32) gather(const int* __restrict__ idx, long long n,
     double* __restrict__ f, double* __restrict__ t_, double* __restrict__ w) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -24,7 +37,8 @@ __global__ void __launch_bounds__(WARPS * 32) gather(const int* __restrict__ idx
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
       const int t = __shfl_sync(0xffffffffu, a, grp * 8 + s);
-      v[s] = __ldg(reinterpret_cast<const int4*>(idx + (long long)t * 32 + sub4));
+      const int4* p = reinterpret_cast<const int4*>(idx + (long long)t * 32 + sub4);
+      v[s] = LD == 1 ? ld_na(p) : (LD == 2 ? ld_ef(p) : __ldg(p));
     }
     int acc = 0;
 #pragma unroll
@@ -48,7 +62,7 @@ int main() {
   CK(cudaMalloc(&idx, n * 32 * 4)); CK(cudaMalloc(&out, 3 * E * 8)); CK(cudaMalloc(&flush, 256 << 20));
   CK(cudaMemcpy(idx, h.data(), n * 32 * 4, cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int cfg = 0; cfg < 6; ++cfg) {
+  for (int cfg = 0; cfg < 8; ++cfg) {
     float tot = 0;
     for (int it = 0; it < 6; ++it) {
       CK(cudaMemset(flush, it, 256 << 20));
@@ -59,12 +73,14 @@ int main() {
         case 2: gather<8, true><<<148 * 8, 256>>>(idx, n, out, out + E, out + 2 * E); break;
         case 3: gather<8, false><<<148 * 8, 256>>>(idx, n, out, out + E, out + 2 * E); break;
         case 4: gather<8, true><<<148 * 3, 256>>>(idx, n, out, out + E, out + 2 * E); break;
-        case 5: gather<8, true><<<148 * 2, 256>>>(idx, n, out, out + E, out + 2 * E); break;
+        case 5: gather<8, true, 1><<<148 * 4, 256>>>(idx, n, out, out + E, out + 2 * E); break;
+        case 6: gather<8, true, 1><<<148 * 8, 256>>>(idx, n, out, out + E, out + 2 * E); break;
+        case 7: gather<8, true, 2><<<148 * 4, 256>>>(idx, n, out, out + E, out + 2 * E); break;
       }
       cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
       float ms; cudaEventElapsedTime(&ms, e0, e1); if (it) tot += ms;
     }
-    const char* nm[] = {"4 CTA/SM write", "6 CTA/SM write", "8 CTA/SM write", "8 CTA/SM read-only", "3 CTA/SM write", "2 CTA/SM write"};
+    const char* nm[] = {"4 CTA/SM write", "6 CTA/SM write", "8 CTA/SM write", "8 CTA/SM read-only", "3 CTA/SM write", "4 CTA/SM no_allocate", "8 CTA/SM no_allocate", "4 CTA/SM ld.global na (coherent)"};
     printf("%-20s %.3f ms  %.2f Gedges/s  %.0f GB/s algorithmic\n", nm[cfg], tot / 5, E / (tot / 5) / 1e6, E * 148.0 / (tot / 5) / 1e6);
   }
   return 0;
