@@ -264,7 +264,13 @@ def run_ours(a):
             def step():
                 pg.step(padded, counts_all, out)
         pg.flags = flags
-        lo, hi = pg.bounds[rank]
+        if a.gather == "peer":  # a contiguous range of this rank's row count, for the kernel-only timing
+            lo = min(pg.plan[0][rank][0], n - pg.rows_of(rank))
+            hi = lo + pg.rows_of(rank)
+            host_share = pg.rows_of(0) / n
+        else:
+            lo, hi = pg.bounds[rank]
+            host_share = (pg.bounds[0][1] - pg.bounds[0][0]) / n
         launches_per_step = None  # counted by pg
 
     def barrier():
@@ -419,7 +425,7 @@ def run_ours(a):
                        "rows over %d ranks, host rank takes %.1f%% (expand/count cost ratio %.3f measured); resident "
                        "replicated int32 index; 4 chunks per rank; u8 counts reach rank 0 %s; expand kernel on rank 0 "
                        "overlapping the next chunk" % (
-                           world, 100.0 * (pg.bounds[0][1] - pg.bounds[0][0]) / n, rho,
+                           world, 100.0 * host_share, rho,
                            "by peer stores from the count kernel's epilogue (CUDA IPC mapping over NVLink, flag per "
                            "chunk)" if a.gather == "peer" else "over NCCL send/recv as counted"),
                        "launch": {"grid": g.value, "block": b.value, "smem": s.value}},
@@ -429,6 +435,9 @@ def run_ours(a):
                          else ("jaccard_wide_k_kernel<%s>" % ("false" if world == 1 else "true")),
                          "bytes_per_edge": bpe, "edges_per_launch": edges_per_launch,
                          "kernel_ms": kern_avg_ms, "peak_source": peak_src},
+            "kernel_only": None if world == 1 else {
+                "value": E / (kern_avg_ms * 1e-3), "unit": UNIT, "ms": kern_avg_ms,
+                "what": "all ranks counting their rows concurrently, slowest rank's kernel; no gather / expand"},
             "clocks": clocks,
             "gpu_launches": launches_per_step * a.steps if world == 1 else int(total_launches * a.steps / (a.steps + max(3, a.warmup))),
             "loop_wall_ms": t_wall * 1e3,

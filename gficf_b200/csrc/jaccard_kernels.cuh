@@ -553,9 +553,9 @@ jaccard_exact_kernel(const int* __restrict__ idx, int k, int kp, long long row_l
 // ---------------------------------------------------------------------------
 // counts -> edge rows, fixed slots (mode 0).  One thread per edge, streaming.
 // ---------------------------------------------------------------------------
-// When `ready` is given, every CTA first waits until *ready >= expected: the counts of this row
-// range are being stored into this GPU's memory by a PEER GPU's count kernel (NVLink stores), and
-// the peer raises the flag (signal_kernel) once that kernel has finished.  A bounded spin: after
+// When `ready` is given, every CTA first waits until ready[0..n_ready) >= expected: the counts of
+// this row range are being stored into this GPU's memory by PEER GPUs' count kernels (NVLink
+// stores), and each peer raises its flag (signal_kernel) once its kernel has finished.  A bounded spin: after
 // ~2^31 clocks the kernel gives up and reports GFICF_FLAG_PEER_TIMEOUT instead of hanging the GPU.
 constexpr unsigned kFlagPeerTimeout = 8u;
 
@@ -565,14 +565,15 @@ template <typename CT>
 __global__ void __launch_bounds__(kExpandThreads)
 expand_fixed_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo, long long row_hi,
                     const CT* d_u, double* __restrict__ o_from, double* __restrict__ o_to,
-                    double* __restrict__ o_w, const volatile unsigned* ready, unsigned expected,
-                    unsigned* flags) {
+                    double* __restrict__ o_w, const volatile unsigned* ready, int n_ready,
+                    unsigned expected, unsigned* flags) {
   __shared__ double lut[256];
   const bool use_lut = k <= 255;
   if (use_lut && (int)threadIdx.x <= k) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
-  if (ready != nullptr && threadIdx.x == 0) {
+  if (ready != nullptr && (int)threadIdx.x < n_ready) {
+    // thread r waits for rank r's flag
     const long long t0 = clock64();
-    while ((int)(*ready - expected) < 0) {
+    while ((int)(ready[threadIdx.x] - expected) < 0) {
       if (clock64() - t0 > (1ll << 31)) {
         atomicOr(flags, kFlagPeerTimeout);
         break;

@@ -261,12 +261,26 @@ class PipelinedGather:
                     self.expand(idx_full, k, counts_all[lo * k:hi * k], lo, hi, out3)
 
 
+def chunk_major_bounds(n: int, world: int, rho: float, chunks: int, host_rank: int = 0):
+    """Row ranges [chunk][rank]: the matrix is cut into `chunks` contiguous pieces; inside each
+    piece the host rank takes the weighted share x (see weighted_bounds) and the other ranks equal
+    parts of the rest.  A chunk is therefore ONE contiguous row range for the host rank's expand."""
+    out = []
+    for c_lo, c_hi in chunk_bounds(0, n, chunks):
+        b = weighted_bounds(c_hi - c_lo, world, rho, host_rank)
+        out.append([(c_lo + lo, c_lo + hi) for lo, hi in b])
+    return out
+
+
 class PeerGather:
-    """The same schedule as PipelinedGather with the gather FUSED into the count kernel: the host
-    rank exports its count buffer (CUDA IPC), the other ranks map it and their count kernels store
-    the 1-byte results straight into the host rank's HBM over NVLink; a flag per rank (raised by a
-    one-thread kernel behind each chunk) tells the host rank's expand kernel that a chunk has
-    landed.  No collective kernel competes for SMs with the persistent count kernels.
+    """Counts on every rank, gather FUSED into the count kernel, expansion on the host rank.
+
+    The host rank exports its count buffer (CUDA IPC); the other ranks map it and their count
+    kernels store the 1-byte results straight into the host rank's HBM over NVLink.  A flag per
+    rank (raised by a one-thread kernel behind each chunk) tells the host rank's expand kernel that
+    a chunk has landed; the expand of chunk c (one launch over the chunk's contiguous rows, waiting
+    for every rank's flag) overlaps everybody's counting of chunk c+1.  No collective kernel
+    competes for SMs with the persistent count kernels.
 
     torch.distributed only carries the 64-byte IPC handle at construction."""
 
@@ -276,9 +290,8 @@ class PeerGather:
         self.D = D
         self.n, self.k, self.group, self.host = n, k, group, host_rank
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.bounds = weighted_bounds(n, self.world, rho, host_rank)
-        self.chunks = [chunk_bounds(lo, hi, chunks) for lo, hi in self.bounds]
-        self.nchunks = chunks
+        self.plan = chunk_major_bounds(n, self.world, rho, chunks, host_rank)
+        self.nchunks = len(self.plan)
         self.epoch = 0
         self.launches = 0
         e = n * k
@@ -294,6 +307,9 @@ class PeerGather:
         self.flags = D.new_flags(torch.device("cuda", torch.cuda.current_device()))
         dist.barrier(group=group)
 
+    def rows_of(self, rank: int) -> int:
+        return sum(p[rank][1] - p[rank][0] for p in self.plan)
+
     def _flag(self, r):
         return self.base + self.flag_off + 4 * r
 
@@ -306,30 +322,24 @@ class PeerGather:
             self.D.ipc_close(self.base)
 
     def step(self, idx_full, out3):
-        D, k, n, C_ = self.D, self.k, self.n, self.nchunks
-        base_val = self.epoch * C_
+        D, k, n = self.D, self.k, self.n
+        base_val = self.epoch * self.nchunks
         ack = self._flag(self.world)
         if self.rank != self.host:
             # the host rank must have consumed the previous step's counts before they are overwritten
             D.wait_flag(ack, self.epoch, self.flags)
-            for c, (lo, hi) in enumerate(self.chunks[self.rank]):
-                if hi > lo:
-                    D.jaccard_counts_to(idx_full, n, k, lo, hi, self.base + lo * k, self.flags)
-                    self.launches += 1
-                D.signal(self._flag(self.rank), base_val + c + 1)
-            self.epoch += 1
-            return
-        for c in range(C_):
-            lo, hi = self.chunks[self.host][c]
+        for c, ranges in enumerate(self.plan):
+            lo, hi = ranges[self.rank]
             if hi > lo:
                 D.jaccard_counts_to(idx_full, n, k, lo, hi, self.base + lo * k, self.flags)
-                D.expand_wait(idx_full, k, lo, hi, self.base + lo * k, out3, 0, 0, self.flags)
-                self.launches += 2
-            for r in range(self.world):
-                lo, hi = self.chunks[r][c]
-                if r != self.host and hi > lo:
-                    D.expand_wait(idx_full, k, lo, hi, self.base + lo * k, out3, self._flag(r), base_val + c + 1,
-                                  self.flags)
+                self.launches += 1
+            D.signal(self._flag(self.rank), base_val + c + 1)
+            if self.rank == self.host:
+                c_lo, c_hi = ranges[0][0], ranges[-1][1]
+                if c_hi > c_lo:
+                    D.expand_wait(idx_full, k, c_lo, c_hi, self.base + c_lo * k, out3, self._flag(0), self.world,
+                                  base_val + c + 1, self.flags)
                     self.launches += 1
         self.epoch += 1
-        D.signal(ack, self.epoch)
+        if self.rank == self.host:
+            D.signal(ack, self.epoch)

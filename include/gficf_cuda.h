@@ -136,7 +136,8 @@ int gficf_cuda_jaccard_rank(const double* idx_colmajor, int64_t n, int32_t k, do
  *  count kernel's epilogue stores its 1-byte results straight into the host
  *  rank's HBM.  gficf_cuda_signal_dev raises a flag in that buffer when the
  *  stream reaches it; gficf_cuda_expand_wait_dev is the expand kernel that first
- *  waits for the flag (bounded spin; GFICF_FLAG_PEER_TIMEOUT on give-up).
+ *  waits until d_ready[0..n_ready) >= expected, one flag per contributing rank
+ *  (bounded spin; GFICF_FLAG_PEER_TIMEOUT on give-up).
  * ======================================================================== */
 #define GFICF_IPC_HANDLE_BYTES 64
 #define GFICF_FLAG_PEER_TIMEOUT 8u
@@ -148,8 +149,8 @@ int gficf_cuda_signal_dev(uint32_t* d_flag, uint32_t value, void* stream);
 int gficf_cuda_wait_dev(const uint32_t* d_flag, uint32_t expected, uint32_t* d_flags, void* stream);
 int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, int64_t row_hi,
                                const uint8_t* d_u, double* d_from, double* d_to, double* d_w,
-                               const uint32_t* d_ready, uint32_t expected, uint32_t* d_flags,
-                               void* stream);
+                               const uint32_t* d_ready, int32_t n_ready, uint32_t expected,
+                               uint32_t* d_flags, void* stream);
 
 /* ======================================================================== *
  *  Device-buffer entry points (resident data: the benchmarked kernels, and

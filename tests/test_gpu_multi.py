@@ -77,7 +77,7 @@ for n, k, dup in ((200_000, 30, False), (10_001, 15, False), (5_000, 100, False)
         assert out is None
 # pipelined gather: uneven split, chunked u8 sends, expand on the host rank
 from gficf_b200 import device as D
-for n, k, rho in ((300_000, 30, 0.19), (50_001, 15, 0.6), (20_000, 100, 0.0)):
+for n, k, rho in ((300_000, 30, 0.19), (50_001, 15, 0.6), (20_000, 100, 0.0), (7, 3, 0.2)):
     idx0 = synth.knn_index(n, k, scramble=True, device="cuda")
     padded, fl = D.pad_rows(idx0)
     pg = sharding.PipelinedGather(n, k, rho=rho, chunks=4)
