@@ -353,6 +353,20 @@ def run_ours(a):
             e2e = {"value": E / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": 24 * E,
                    "ms_per_step": dt * 1e3, "call": "gficf_b200.rcpp_parallel_jaccard_coef (pinned host buffers)",
                    "breakdown_ms": {kk: round(v, 3) for kk, v in tm.items() if kk != "reserved"}}
+            # the same call on ordinary pageable memory (what R hands over): staged through pinned slots
+            r_page = np.asfortranarray(np.array(r_host))
+            out_page = np.zeros((E, 3), dtype=np.float64, order="F")
+            gficf_b200.rcpp_parallel_jaccard_coef(r_page, False, 1, out=out_page)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                gficf_b200.rcpp_parallel_jaccard_coef(r_page, False, 1, out=out_page)
+            dtp = (time.perf_counter() - t0) / 3
+            e2e["pageable"] = {"value": E / dtp, "ms_per_step": dtp * 1e3,
+                               "matches_pinned": bool(np.array_equal(out_page[: 10**6], np.asarray(out_host)[: 10**6])
+                                                      and np.array_equal(out_page[-10**6:], np.asarray(out_host)[-10**6:])),
+                               "breakdown_ms": {kk: round(v, 3) for kk, v in gficf_b200.last_timings().items()
+                                                if kk != "reserved"}}
+            del r_page, out_page
         else:
             # one process per GPU on SHARED host matrices: every rank moves its own rows over its
             # own PCIe link (gficf_cuda_jaccard_rank); rank 0 owns / fills / checks the matrices

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -294,7 +295,8 @@ struct PinBuf {
 };
 
 constexpr int kMaxChunks = 32;
-constexpr size_t kStageBytes = 32u << 20;  // pinned bounce buffer (x2 per direction)
+constexpr size_t kStageChunk = 4u << 20;  // pageable host memory moves in pieces of this size
+constexpr int kStageSlots = 16;           // through a ring of pinned slots (64 MiB per device)
 
 struct DeviceWs {
   int dev = -1;
@@ -304,8 +306,8 @@ struct DeviceWs {
   cudaEvent_t ev_chunk[kMaxChunks] = {};
   cudaEvent_t ev_k0[kMaxChunks] = {}, ev_k1[kMaxChunks] = {};
   Buf in_f64, idx, out, counts, scratch, small;  // small: flags (4B) + n_written (8B)
-  PinBuf stage[2];
-  cudaEvent_t ev_stage[2] = {};
+  PinBuf ring;
+  cudaEvent_t ev_slot[kStageSlots] = {};
   unsigned* h_small = nullptr;  // pinned mirror of `small`
 
   void ensure(int d) {
@@ -318,7 +320,7 @@ struct DeviceWs {
     for (auto& e : ev_chunk) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : ev_k0) CU_TRY(cudaEventCreate(&e));
     for (auto& e : ev_k1) CU_TRY(cudaEventCreate(&e));
-    for (auto& e : ev_stage) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ev_slot) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     small.need(64);
     CU_TRY(cudaHostAlloc((void**)&h_small, 64, cudaHostAllocDefault));
     init = true;
@@ -328,14 +330,14 @@ struct DeviceWs {
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
     in_f64.drop(); idx.drop(); out.drop(); counts.drop(); scratch.drop(); small.drop();
-    stage[0].drop(); stage[1].drop();
+    ring.drop();
     if (h_small) cudaFreeHost(h_small);
     h_small = nullptr;
     for (auto& e : ev) cudaEventDestroy(e);
     for (auto& e : ev_chunk) cudaEventDestroy(e);
     for (auto& e : ev_k0) cudaEventDestroy(e);
     for (auto& e : ev_k1) cudaEventDestroy(e);
-    for (auto& e : ev_stage) cudaEventDestroy(e);
+    for (auto& e : ev_slot) cudaEventDestroy(e);
     cudaStreamDestroy(s_comp);
     cudaStreamDestroy(s_copy);
     init = false;
@@ -391,10 +393,128 @@ bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// Host -> device of a strided 2-D block (rows x cols doubles, source leading
-// dimension ld_src, destination dense with leading dimension rows).  Pinned
-// sources go straight to the copy engine; pageable ones are staged through two
-// pinned bounce buffers so the host memcpy overlaps the DMA.
+// ------------------------------------------------------------------ pageable host memory
+// R hands over ordinary (pageable) memory.  cudaMemcpy on pageable memory is a single-threaded
+// staging copy; here the transfer is cut into kStageChunk pieces that go through a ring of pinned
+// slots, the host-side memcpy of the pieces is done by a few worker threads in parallel, and the
+// DMA of piece j overlaps the memcpy of its neighbours.
+struct Seg {
+  char* host;
+  char* dev;
+  size_t bytes;
+  cudaEvent_t wait_before;  // the copy stream waits for this event before the segment (or null)
+};
+
+std::atomic<int> g_active_devices{1};  // devices of the running host-level call (they share the cores)
+
+int copy_threads() {
+  static int t = [] {
+    const char* e = getenv("GFICF_CUDA_COPY_THREADS");
+    int v = e ? atoi(e) : 0;
+    if (v <= 0) {
+      // measured on a 16-thread host (4M x 30, pageable in/out): 2 threads 248 ms, 4: 137, 8: 94,
+      // 12: 90, 16: 111 (pinned buffers: 72 ms)
+      v = (int)std::thread::hardware_concurrency() / 2;
+      v = std::max(2, std::min(12, v));
+    }
+    return v;
+  }();
+  return std::max(2, t / std::max(1, g_active_devices.load()));
+}
+
+struct Piece {
+  char* host;
+  char* dev;
+  size_t bytes;
+  cudaEvent_t wait_before;
+};
+
+void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cudaStream_t st) {
+  std::vector<Piece> pieces;
+  for (const Seg& g : segs) {
+    bool first = true;
+    for (size_t off = 0; off < g.bytes; off += kStageChunk) {
+      pieces.push_back({g.host + off, g.dev + off, std::min(kStageChunk, g.bytes - off),
+                        first ? g.wait_before : nullptr});
+      first = false;
+    }
+  }
+  const int np = (int)pieces.size();
+  if (!np) return;
+  ws.ring.need(kStageChunk * kStageSlots);
+  char* ring = (char*)ws.ring.p;
+  std::vector<std::atomic<int>> host_done(np), dma_issued(np);
+  for (int j = 0; j < np; ++j) {
+    host_done[j].store(0);
+    dma_issued[j].store(0);
+  }
+  std::atomic<int> next(0);
+  std::atomic<bool> failed(false);
+  const int dev = ws.dev;
+  const int nthreads = std::min(copy_threads(), np);
+  auto worker = [&]() {
+    cudaSetDevice(dev);
+    for (;;) {
+      const int j = next.fetch_add(1);
+      if (j >= np || failed.load()) return;
+      const Piece& pc = pieces[j];
+      char* slot = ring + (size_t)(j % kStageSlots) * kStageChunk;
+      if (to_device) {
+        // the slot is free once the DMA of piece j - kStageSlots has completed
+        if (j >= kStageSlots) {
+          while (!dma_issued[j - kStageSlots].load(std::memory_order_acquire)) {
+            if (failed.load()) return;
+            std::this_thread::yield();
+          }
+          if (cudaEventSynchronize(ws.ev_slot[j % kStageSlots]) != cudaSuccess) failed.store(true);
+        }
+        memcpy(slot, pc.host, pc.bytes);
+        host_done[j].store(1, std::memory_order_release);
+      } else {
+        while (!dma_issued[j].load(std::memory_order_acquire)) {
+          if (failed.load()) return;
+          std::this_thread::yield();
+        }
+        if (cudaEventSynchronize(ws.ev_slot[j % kStageSlots]) != cudaSuccess) failed.store(true);
+        memcpy(pc.host, slot, pc.bytes);
+        host_done[j].store(1, std::memory_order_release);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+  cudaError_t err = cudaSuccess;
+  for (int j = 0; j < np && err == cudaSuccess; ++j) {
+    const Piece& pc = pieces[j];
+    char* slot = ring + (size_t)(j % kStageSlots) * kStageChunk;
+    if (pc.wait_before) err = cudaStreamWaitEvent(st, pc.wait_before, 0);
+    if (to_device) {
+      while (!host_done[j].load(std::memory_order_acquire)) std::this_thread::yield();
+      if (err == cudaSuccess) err = cudaMemcpyAsync(pc.dev, slot, pc.bytes, cudaMemcpyHostToDevice, st);
+    } else {
+      // the slot is free once piece j - kStageSlots has been copied out by a worker
+      if (j >= kStageSlots)
+        while (!host_done[j - kStageSlots].load(std::memory_order_acquire)) std::this_thread::yield();
+      if (err == cudaSuccess) err = cudaMemcpyAsync(slot, pc.dev, pc.bytes, cudaMemcpyDeviceToHost, st);
+    }
+    if (err == cudaSuccess) err = cudaEventRecord(ws.ev_slot[j % kStageSlots], st);
+    dma_issued[j].store(1, std::memory_order_release);
+  }
+  if (err != cudaSuccess) {
+    failed.store(true);
+    for (int j = 0; j < np; ++j) {
+      dma_issued[j].store(1);
+      host_done[j].store(1);
+    }
+  }
+  for (auto& t : pool) t.join();
+  if (err != cudaSuccess || failed.load())
+    throw Err{GFICF_E_CUDA, fmt("staged host copy failed: %s", cudaGetErrorString(err))};
+}
+
+// Host -> device of a strided 2-D block (rows x cols doubles, source leading dimension ld_src,
+// destination dense with leading dimension rows).  Pinned sources go straight to the copy
+// engine; pageable ones through staged_copy.
 void h2d_block(DeviceWs& ws, const double* src, long long ld_src, double* dst, long long rows,
                int cols, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return;
@@ -403,56 +523,25 @@ void h2d_block(DeviceWs& ws, const double* src, long long ld_src, double* dst, l
                              rows * sizeof(double), cols, cudaMemcpyHostToDevice, st));
     return;
   }
-  ws.stage[0].need(kStageBytes);
-  ws.stage[1].need(kStageBytes);
-  const long long per = kStageBytes / sizeof(double);
-  int b = 0;
-  for (int c = 0; c < cols; ++c) {
-    for (long long r0 = 0; r0 < rows; r0 += per) {
-      const long long m = std::min(per, rows - r0);
-      CU_TRY(cudaEventSynchronize(ws.ev_stage[b]));
-      memcpy(ws.stage[b].p, src + (long long)c * ld_src + r0, m * sizeof(double));
-      CU_TRY(cudaMemcpyAsync(dst + (long long)c * rows + r0, ws.stage[b].p, m * sizeof(double),
-                             cudaMemcpyHostToDevice, st));
-      CU_TRY(cudaEventRecord(ws.ev_stage[b], st));
-      b ^= 1;
-    }
-  }
+  std::vector<Seg> segs;
+  for (int c = 0; c < cols; ++c)
+    segs.push_back({(char*)(src + (long long)c * ld_src), (char*)(dst + (long long)c * rows),
+                    (size_t)rows * sizeof(double), nullptr});
+  staged_copy(ws, segs, true, st);
 }
 
-// Device -> host of a contiguous run.  Pageable destinations are staged.
-void d2h_run(DeviceWs& ws, double* dst, const double* src, long long count, cudaStream_t st) {
-  if (count <= 0) return;
-  if (is_pinned(dst)) {
-    CU_TRY(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+// Device -> host of contiguous runs (each optionally behind an event).  Pinned destinations:
+// plain async copies; pageable ones: staged_copy.
+void d2h_segs(DeviceWs& ws, const std::vector<Seg>& segs, cudaStream_t st) {
+  if (segs.empty()) return;
+  if (is_pinned(segs[0].host)) {
+    for (const Seg& g : segs) {
+      if (g.wait_before) CU_TRY(cudaStreamWaitEvent(st, g.wait_before, 0));
+      if (g.bytes) CU_TRY(cudaMemcpyAsync(g.host, g.dev, g.bytes, cudaMemcpyDeviceToHost, st));
+    }
     return;
   }
-  ws.stage[0].need(kStageBytes);
-  ws.stage[1].need(kStageBytes);
-  const long long per = kStageBytes / sizeof(double);
-  // two-deep pipeline: DMA chunk c+1 into one bounce buffer while memcpy-ing chunk c out
-  long long pend_off[2] = {-1, -1}, pend_cnt[2] = {0, 0};
-  int b = 0;
-  for (long long off = 0; off < count; off += per) {
-    const long long m = std::min(per, count - off);
-    if (pend_off[b] >= 0) {
-      CU_TRY(cudaEventSynchronize(ws.ev_stage[b]));
-      memcpy(dst + pend_off[b], ws.stage[b].p, pend_cnt[b] * sizeof(double));
-    }
-    CU_TRY(cudaMemcpyAsync(ws.stage[b].p, src + off, m * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaEventRecord(ws.ev_stage[b], st));
-    pend_off[b] = off;
-    pend_cnt[b] = m;
-    b ^= 1;
-  }
-  for (int q = 0; q < 2; ++q) {
-    if (pend_off[b] >= 0) {
-      CU_TRY(cudaEventSynchronize(ws.ev_stage[b]));
-      memcpy(dst + pend_off[b], ws.stage[b].p, pend_cnt[b] * sizeof(double));
-      pend_off[b] = -1;
-    }
-    b ^= 1;
-  }
+  staged_copy(ws, segs, false, st);
 }
 
 struct SlabResult {
@@ -494,9 +583,12 @@ void d2h_slab(DeviceWs& ws, const Slab& s, SlabResult* res) {
   double* d_to = d_from + s.slab_e;
   double* d_w = d_to + s.slab_e;
   CU_TRY(cudaEventRecord(ws.ev[4], ws.s_copy));
-  d2h_run(ws, s.h_out + s.lo * s.k, d_from, s.slab_e, ws.s_copy);
-  d2h_run(ws, s.h_out + s.E + s.lo * s.k, d_to, s.slab_e, ws.s_copy);
-  d2h_run(ws, s.h_out + 2 * s.E + s.lo * s.k, d_w, s.slab_e, ws.s_copy);
+  const size_t bytes = (size_t)s.slab_e * sizeof(double);
+  d2h_segs(ws,
+           {{(char*)(s.h_out + s.lo * s.k), (char*)d_from, bytes, nullptr},
+            {(char*)(s.h_out + s.E + s.lo * s.k), (char*)d_to, bytes, nullptr},
+            {(char*)(s.h_out + 2 * s.E + s.lo * s.k), (char*)d_w, bytes, nullptr}},
+           ws.s_copy);
   CU_TRY(cudaEventRecord(ws.ev[5], ws.s_copy));
   CU_TRY(cudaStreamSynchronize(ws.s_copy));
   float ms = 0;
@@ -560,14 +652,16 @@ void device_phase1(Slab s, SlabResult* res) {
       }
       CU_TRY(cudaStreamWaitEvent(ws.s_copy, ws.ev[3], 0));
       CU_TRY(cudaEventRecord(ws.ev[4], ws.s_copy));
+      std::vector<Seg> segs;
       for (int c = 0; c < used; ++c) {
         const long long clo = s.lo + c * rpc, chi = std::min(s.hi, clo + rpc);
-        const long long eo = (clo - s.lo) * k, ce = (chi - clo) * k;
-        CU_TRY(cudaStreamWaitEvent(ws.s_copy, ws.ev_chunk[c], 0));
-        d2h_run(ws, s.h_out + s.lo * k + eo, d_from + eo, ce, ws.s_copy);
-        d2h_run(ws, s.h_out + s.E + s.lo * k + eo, d_to + eo, ce, ws.s_copy);
-        d2h_run(ws, s.h_out + 2 * s.E + s.lo * k + eo, d_w + eo, ce, ws.s_copy);
+        const long long eo = (clo - s.lo) * k;
+        const size_t cb = (size_t)(chi - clo) * k * sizeof(double);
+        segs.push_back({(char*)(s.h_out + s.lo * k + eo), (char*)(d_from + eo), cb, ws.ev_chunk[c]});
+        segs.push_back({(char*)(s.h_out + s.E + s.lo * k + eo), (char*)(d_to + eo), cb, nullptr});
+        segs.push_back({(char*)(s.h_out + 2 * s.E + s.lo * k + eo), (char*)(d_w + eo), cb, nullptr});
       }
+      d2h_segs(ws, segs, ws.s_copy);
       CU_TRY(cudaEventRecord(ws.ev[5], ws.s_copy));
     } else if (fast_ok && s.slab_e > 0) {
       ws.counts.need(std::max<size_t>(16, (size_t)s.slab_e * cbytes));
@@ -773,6 +867,7 @@ int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int
   cudaGetDevice(&prev_dev);
   const auto t0 = std::chrono::steady_clock::now();
   const long long rows_per = (n + ndev - 1) / ndev;
+  g_active_devices.store(ndev);
   std::vector<SlabResult> res(ndev);
   std::vector<Slab> slabs;
   for (int r = 0; r < ndev; ++r) slabs.emplace_back(r, ndev, idx, (long long)n, (int)k, rows_per, out, (int)mode);

@@ -1,14 +1,18 @@
 #!/bin/bash
-# One GPU-box session: smoke, GPU tests, bench, ncu launch list + full capture of the main kernel.
+# One GPU-box session: smoke, GPU tests, bench (+reference arm), ncu launch list + full captures.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt; lscpu | grep 'Model name' >> gpurun_out/gpu.txt
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/summary.txt
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee gpurun_out/summary.txt
 timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/summary.txt
-tail -5 gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" | tee -a gpurun_out/summary.txt
 cat gpurun_out/bench.json
+if [ "$1" = "full" ]; then
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$?" | tee -a gpurun_out/summary.txt
 cat gpurun_out/bench_ref.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?" | tee -a gpurun_out/summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:jaccard_small_k -s 3 -c 2 -o gpurun_out/prof_small_k -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" | tee -a gpurun_out/summary.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?" | tee -a gpurun_out/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:jaccard_small_k -s 3 -c 1 -o gpurun_out/prof_small_k_final -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" | tee -a gpurun_out/summary.txt
+timeout 900 python bench.py --cells 1000000 --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_1m.json 2>/dev/null; cat gpurun_out/bench_1m.json
+timeout 900 python bench.py --cells 10000000 --k 100 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_cfg5_n1.json 2>/dev/null; cat gpurun_out/bench_cfg5_n1.json
+fi
