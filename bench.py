@@ -425,6 +425,15 @@ def run_ours(a):
         got = out[:, : ref_rows * k].cpu().numpy().T
         cpu["gpu_matches_on_sample"] = bool(np.array_equal(got, chk))
 
+    traffic = None
+    try:  # ncu-measured DRAM bytes per launch of this exact kernel/workload, if a capture was committed
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        key = ("jaccard_small_k_kernel<32,false>" if 16 < k <= 32 else "jaccard_wide_k_kernel<false>") + \
+            " cells=%d k=%d" % (n, k)
+        if world == 1 and key in tj:
+            traffic = tj[key]["traffic_bytes"]
+    except Exception:
+        pass
     if rank == 0:
         g, b, s, v = (C_int32() for _ in range(4))
         gficf_b200.lib().gficf_cuda_last_launch(g, b, s, v)
@@ -444,7 +453,7 @@ def run_ours(a):
                            "chunk)" if a.gather == "peer" else "over NCCL send/recv as counted"),
                        "launch": {"grid": g.value, "block": b.value, "smem": s.value}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
+                         "frac": achieved / hbm_peak, "traffic": traffic,
                          "kernel": ("jaccard_small_k_kernel<%d,%s>" % (D.row_stride(k), "false" if world == 1 else "true")) if k <= 32
                          else ("jaccard_wide_k_kernel<%s>" % ("false" if world == 1 else "true")),
                          "bytes_per_edge": bpe, "edges_per_launch": edges_per_launch,

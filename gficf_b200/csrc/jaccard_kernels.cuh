@@ -33,6 +33,9 @@
 #ifndef GFICF_SMALL_LOG_TS32
 #define GFICF_SMALL_LOG_TS32 9   // hash-table slots per warp for 16 < k <= 32: 2^9
 #endif
+#ifndef GFICF_SMALL_MATCH
+#define GFICF_SMALL_MATCH 0      // k<=32: find hash collisions with match.any (1; measured slower: 3.12 vs 3.07 ms at k=30, 1.95 vs 1.55 ms at k=15) or through the table (0)
+#endif
 #ifndef GFICF_SMALL_WARPS
 #define GFICF_SMALL_WARPS 7      // warps (rows in flight) per CTA of the k<=32 kernel
 #endif
@@ -250,6 +253,29 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     unsigned mult = kMult0, slot;
     bool dup = false;
     int tries = 0;
+#if GFICF_SMALL_MATCH
+    // Collisions are found in registers: lanes whose ids hash to the same slot find each other
+    // with match.any; a group whose ids differ from its leader's is a collision (try the next
+    // multiplier), a group with equal ids is a repeated id.  No shared-memory traffic per try.
+    for (;;) {
+      slot = ((unsigned)a * mult) >> SHIFT;
+      const unsigned peers = __match_any_sync(kFull, valid ? slot : (0x80000000u | (unsigned)lane));
+      const int leader = __ffs(peers) - 1;
+      const int lkey = __shfl_sync(kFull, a, leader);
+      const bool follower = valid && lane != leader;  // shares its slot with a lower lane
+      dup |= follower && lkey == a;
+      if (!__any_sync(kFull, follower && lkey != a)) break;
+      if (++tries == kMaxTries) {
+        warp_flags |= kFlagHashFail;
+        break;
+      }
+      mult = next_mult(mult);
+    }
+#else
+    // Collisions are found through the table: every lane stores its lane id in its slot and reads
+    // it back.  Lanes of one warp that hash to the same slot store DIFFERENT values to it in the
+    // same instruction on purpose -- whichever 32-bit store lands, all the others read a foreign
+    // id and report the collision (compute-sanitizer's racecheck flags this write-write hazard).
     for (;;) {
       slot = ((unsigned)a * mult) >> SHIFT;
       if (valid) tbl[slot] = (unsigned)lane;
@@ -264,10 +290,12 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
         warp_flags |= kFlagHashFail;
         break;
       }
+      __syncwarp();
       if (valid) tbl[slot] = kEmpty;
       __syncwarp();
       mult = next_mult(mult);
     }
+#endif
     if (valid) tbl[slot] = (unsigned)a;
     if (__any_sync(kFull, dup)) warp_flags |= kFlagDupId;
     __syncwarp();

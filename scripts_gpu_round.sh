@@ -16,3 +16,23 @@ timeout 900 ncu --set full --clock-control none --import-source on --profile-fro
 timeout 900 python bench.py --cells 1000000 --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_1m.json 2>/dev/null; cat gpurun_out/bench_1m.json
 timeout 900 python bench.py --cells 10000000 --k 100 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_cfg5_n1.json 2>/dev/null; cat gpurun_out/bench_cfg5_n1.json
 fi
+if [ "$1" = "full" ]; then
+# race / memory checks of the hand-written kernels on small inputs (shared-memory hash tables, warp-synchronous code)
+cat > /tmp/sanitize_case.py <<'PY'
+import numpy as np, sys
+sys.path.insert(0, '.')
+import gficf_b200
+from oracle.binding import Oracle
+from tests.conftest import random_knn
+orc = Oracle(); rng = np.random.default_rng(0)
+for n, k, distinct in ((3000, 30, True), (2000, 15, True), (600, 100, True), (500, 64, True), (300, 30, False), (200, 7, True)):
+    idx = random_knn(rng, n, k, distinct=distinct)
+    assert np.array_equal(gficf_b200.rcpp_parallel_jaccard_coef(idx), orc.parallel(idx)), (n, k)
+    assert np.array_equal(gficf_b200.jaccard_coeff(idx), orc.serial(idx)), (n, k)
+print("SANITIZE_CASE_OK")
+PY
+for tool in memcheck racecheck; do
+timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/sanitize_case.py > gpurun_out/sanitizer_$tool.log 2>&1; echo "sanitizer $tool rc=$?" | tee -a gpurun_out/summary.txt
+grep -E "ERROR SUMMARY|RACECHECK SUMMARY|SANITIZE_CASE_OK|Race reported|Invalid" gpurun_out/sanitizer_$tool.log | head -5
+done
+fi
