@@ -153,10 +153,37 @@ void launch_wide(const int* idx, int k, int kp, long long lo, long long hi, doub
   tl_launch = {grid, block, (int)smem, 1000 + LOG_TS};
 }
 
+template <bool CO>
+void launch_large(const int* idx, int k, int kp, long long lo, long long hi, double* f, double* t,
+                  double* w, void* u, unsigned* flags, cudaStream_t st) {
+  const size_t smem = large_smem_bytes();
+  const int block = kLargeWarps * 32;
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  static thread_local bool attr_set[64][2] = {};
+  auto k8 = jaccard_large_k_kernel<uint8_t, CO>;
+  auto k16 = jaccard_large_k_kernel<uint16_t, CO>;
+  if (!attr_set[dev & 63][CO]) {
+    CU_TRY(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev & 63][CO] = true;
+  }
+  if (k <= 255) {
+    const int grid = persistent_grid(k8, block, smem, hi - lo);
+    k8<<<grid, block, smem, st>>>(idx, k, kp, lo, hi, f, t, w, (uint8_t*)u, flags);
+    tl_launch = {grid, block, (int)smem, 2000};
+  } else {
+    const int grid = persistent_grid(k16, block, smem, hi - lo);
+    k16<<<grid, block, smem, st>>>(idx, k, kp, lo, hi, f, t, w, (uint16_t*)u, flags);
+    tl_launch = {grid, block, (int)smem, 2001};
+  }
+}
+
 // fast kernels; returns false when k is outside their range
 template <bool CO>
 bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
-                 uint8_t* u, unsigned* flags, cudaStream_t st) {
+                 void* u_any, unsigned* flags, cudaStream_t st) {
+  uint8_t* u = (uint8_t*)u_any;  // one byte per edge for k <= 255, two above
   if (hi <= lo) return true;
   const int kp = row_stride(k);
   if (k <= 4) launch_small<4, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
@@ -170,6 +197,8 @@ bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, d
       case 12: launch_wide<12, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
       default: launch_wide<13, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
     }
+  } else if (k <= kLargeMaxK) {
+    launch_large<CO>(idx, k, kp, lo, hi, f, t, w, u_any, flags, st);
   } else {
     return false;
   }
@@ -189,22 +218,14 @@ void launch_layout(const double* src, long long ld_rows, long long ld_row0, long
                    long long lo, long long hi, int* dst, unsigned* flags, cudaStream_t st) {
   if (hi <= lo) return;
   const int kp = row_stride(k);
-  const size_t smem = (size_t)kLayoutTileR * (kp + 1) * sizeof(int);
-  if (smem > 48 * 1024) {
-    static thread_local bool attr_set[64] = {};
-    int dev = 0;
-    CU_TRY(cudaGetDevice(&dev));
-    if (!attr_set[dev & 63]) {
-      CU_TRY(cudaFuncSetAttribute(layout_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  200 * 1024));
-      attr_set[dev & 63] = true;
-    }
-    if (smem > 200 * 1024) throw Err{GFICF_E_LIMIT, "k too large for the layout pre-pass tile"};
-  }
-  const long long ntiles = (hi - lo + kLayoutTileR - 1) / kLayoutTileR;
+  int tile_r = kLayoutTileR;
+  while (tile_r > 1 && (size_t)tile_r * (kp + 1) * sizeof(int) > 48 * 1024) tile_r /= 2;
+  const size_t smem = (size_t)tile_r * (kp + 1) * sizeof(int);
+  if (smem > 48 * 1024) throw Err{GFICF_E_LIMIT, "k too large for the layout pre-pass (k <= 12000)"};
+  const long long ntiles = (hi - lo + tile_r - 1) / tile_r;
   long long g = std::min<long long>(ntiles, (long long)sm_count() * 8);
   layout_f64_kernel<<<(int)g, kLayoutThreads, smem, st>>>(src, ld_rows, ld_row0, n, k, kp, lo, hi, dst,
-                                                          flags);
+                                                          flags, tile_r);
   CU_TRY(cudaGetLastError());
 }
 
@@ -629,7 +650,7 @@ void device_phase1(Slab s, SlabResult* res) {
     CU_TRY(cudaEventRecord(ws.ev[3], ws.s_comp));
 
     const int* d_idx = (const int*)ws.idx.p;
-    const bool fast_ok = k <= 128;
+    const bool fast_ok = k <= kLargeMaxK;
     double* d_from = (double*)ws.out.p;
     double* d_to = d_from + s.slab_e;
     double* d_w = d_to + s.slab_e;
@@ -666,7 +687,7 @@ void device_phase1(Slab s, SlabResult* res) {
     } else if (fast_ok && s.slab_e > 0) {
       ws.counts.need(std::max<size_t>(16, (size_t)s.slab_e * cbytes));
       CU_TRY(cudaEventRecord(ws.ev_k0[0], ws.s_comp));
-      launch_fast<true>(d_idx, k, s.lo, s.hi, nullptr, nullptr, nullptr, (uint8_t*)ws.counts.p, d_flags,
+      launch_fast<true>(d_idx, k, s.lo, s.hi, nullptr, nullptr, nullptr, ws.counts.p, d_flags,
                         ws.s_comp);
       CU_TRY(cudaEventRecord(ws.ev_k1[0], ws.s_comp));
       res->launches++;
@@ -889,7 +910,7 @@ int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int
   bool bad_id = (all_flags & kFlagBadId) != 0;
   if (!bad_id) {
     first_error();
-    const bool exact = k > 128 || (all_flags & (kFlagDupId | kFlagHashFail));
+    const bool exact = k > kLargeMaxK || (all_flags & (kFlagDupId | kFlagHashFail));
     if (exact || mode == GFICF_MODE_SERIAL) {
       if (ndev == 1) {
         device_phase2(slabs[0], exact, &res[0]);
@@ -1004,7 +1025,7 @@ int gficf_cuda_jaccard_rank(const double* idx, int64_t n, int32_t k, double* out
   if (all_flags & kFlagBadId)
     throw Err{GFICF_E_RANGE,
               "neighbour ids must be integers in [1, nrow] (NaN, fractional or out-of-range id found)"};
-  if (k > 128 || (all_flags & (kFlagDupId | kFlagHashFail))) {
+  if (k > kLargeMaxK || (all_flags & (kFlagDupId | kFlagHashFail))) {
     device_phase2(s, true, &res);
     if (res.err.code != GFICF_OK) throw res.err;
   }
@@ -1156,7 +1177,7 @@ int gficf_cuda_jaccard_counts_dev(const int32_t* d_idx_i32, int64_t n, int32_t k
                                   int64_t row_hi, uint8_t* d_u, uint32_t* d_flags, void* stream) {
   DEV_BEGIN
   if (!d_idx_i32 || !d_u || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
-  if (!launch_fast<true>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, d_u, d_flags,
+  if (!launch_fast<true>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u, d_flags,
                          (cudaStream_t)stream))
     return GFICF_E_LIMIT;
   return GFICF_OK;

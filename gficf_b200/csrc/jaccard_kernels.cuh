@@ -120,24 +120,24 @@ __device__ __forceinline__ double jaccard_weight(int u, int k) {
 // shared-memory tile, then the tile (contiguous in the output) leaves with 16-byte
 // stores.
 // ---------------------------------------------------------------------------
-constexpr int kLayoutTileR = 64;
+constexpr int kLayoutTileR = 64;  // rows per tile (halved by the host until the tile fits 48 KB)
 constexpr int kLayoutThreads = 256;
 
 __global__ void __launch_bounds__(kLayoutThreads)
 layout_f64_kernel(const double* __restrict__ src, long long ld_rows, long long ld_row0, long long n,
                   int k, int kp, long long row_lo, long long row_hi, int* __restrict__ dst,
-                  unsigned* __restrict__ flags) {
-  extern __shared__ int tile[];  // [kLayoutTileR][kp + 1]
+                  unsigned* __restrict__ flags, int tile_r) {
+  extern __shared__ int tile[];  // [tile_r][kp + 1]
   const int tid = threadIdx.x;
   const int stride = kp + 1;
-  const long long ntiles = (row_hi - row_lo + kLayoutTileR - 1) / kLayoutTileR;
+  const long long ntiles = (row_hi - row_lo + tile_r - 1) / tile_r;
   bool bad = false;
   for (long long tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
-    const long long r0 = row_lo + tb * kLayoutTileR;
-    const int rows = (int)min((long long)kLayoutTileR, row_hi - r0);
-    // column reads: thread -> (row r = tid % 64, column group tid / 64)
-    const int r = tid & (kLayoutTileR - 1);
-    for (int j = tid / kLayoutTileR; j < kp; j += kLayoutThreads / kLayoutTileR) {
+    const long long r0 = row_lo + tb * tile_r;
+    const int rows = (int)min((long long)tile_r, row_hi - r0);
+    // column reads: thread -> (row r = tid % tile_r, column group tid / tile_r); tile_r is a power of 2
+    const int r = tid & (tile_r - 1);
+    for (int j = tid / tile_r; j < kp; j += kLayoutThreads / tile_r) {
       int v = kPadId;
       if (j < k && r < rows) {
         const double d = __ldcs(src + (long long)j * ld_rows + (r0 + r - ld_row0));
@@ -546,6 +546,114 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
   }
   if (COUNTS_ONLY) __threadfence_system();  // the counts may live in a peer GPU's memory
   if (warp_flags && lane == 0) atomicOr(flags, warp_flags);
+}
+
+// ---------------------------------------------------------------------------
+// Fast kernel, 128 < k <= 1024: a CTA of 8 warps owns row i.  A collision-free table would need
+// ~k^2/2 slots, so membership is tested in an open-addressing table (4096 slots, load <= 0.25,
+// linear probing: 1.2 probes on average).  Each warp takes every 8th edge; one neighbour row is
+// fetched with up to 8 LDG.128 per lane.
+// ---------------------------------------------------------------------------
+constexpr int kLargeWarps = 8;
+constexpr int kLargeMaxK = 1024;
+constexpr int kLargeLogTs = 12;
+constexpr int kLargeChunks = kLargeMaxK / 128;  // 16-byte pieces per lane per neighbour row
+
+__host__ __device__ constexpr size_t large_smem_bytes() {
+  return ((size_t)(1 << kLargeLogTs) + kLargeMaxK + kLargeMaxK / 2) * 4 + (kLargeMaxK + 1) * 8 + 16;
+}
+
+template <typename CT, bool COUNTS_ONLY>
+__global__ void __launch_bounds__(kLargeWarps * 32)
+jaccard_large_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo, long long row_hi,
+                       double* __restrict__ o_from, double* __restrict__ o_to,
+                       double* __restrict__ o_w, CT* __restrict__ o_u, unsigned* __restrict__ flags) {
+  constexpr int TS = 1 << kLargeLogTs, SHIFT = 32 - kLargeLogTs;
+  extern __shared__ unsigned smem_u[];
+  unsigned* tbl = smem_u;                                              // [TS]
+  int* srow = reinterpret_cast<int*>(tbl + TS);                         // [1024] ids of row i
+  unsigned short* scnt = reinterpret_cast<unsigned short*>(srow + kLargeMaxK);  // [1024] u per edge
+  double* lut = reinterpret_cast<double*>(srow + kLargeMaxK + kLargeMaxK / 2 + 2);  // [k+1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int x = tid; x <= k; x += blockDim.x) lut[x] = jaccard_weight(x, k);
+  const int nchunk = (kp + 127) / 128;
+  const char* lane_base = reinterpret_cast<const char*>(idx + lane * 4);
+  const unsigned row_bytes = (unsigned)kp * 4u;
+  bool dup = false;
+
+  for (long long row = row_lo + blockIdx.x; row < row_hi; row += gridDim.x) {
+    for (int x = tid; x < TS; x += blockDim.x) tbl[x] = kEmpty;
+    for (int x = tid; x < kp; x += blockDim.x) srow[x] = __ldg(idx + row * (long long)kp + x);
+    __syncthreads();
+    // ---- insert N(i): linear probing, a slot is claimed with a shared-memory CAS
+    for (int x = tid; x < k; x += blockDim.x) {
+      const unsigned key = (unsigned)srow[x];
+      unsigned s = (key * kMult0) >> SHIFT;
+      for (;;) {
+        const unsigned old = atomicCAS(&tbl[s], kEmpty, key);
+        if (old == kEmpty) break;
+        if (old == key) {  // the row lists this id twice
+          dup = true;
+          break;
+        }
+        s = (s + 1) & (TS - 1);
+      }
+    }
+    __syncthreads();
+    // ---- edges e = warp, warp+8, ...
+    for (int e = warp; e < k; e += kLargeWarps) {
+      const unsigned t = (unsigned)srow[e];
+      int4 v[kLargeChunks];
+#pragma unroll
+      for (int c = 0; c < kLargeChunks; ++c) {
+        v[c] = make_int4(kPadId, kPadId, kPadId, kPadId);
+        if (c < nchunk && c * 128 + lane * 4 < kp)
+          v[c] = __ldg(reinterpret_cast<const int4*>(lane_base + (unsigned long long)t * row_bytes + c * 512));
+      }
+      int cnt = 0;
+#pragma unroll
+      for (int c = 0; c < kLargeChunks; ++c) {
+        if (c < nchunk) {  // block-uniform
+          const unsigned xs[4] = {(unsigned)v[c].x, (unsigned)v[c].y, (unsigned)v[c].z, (unsigned)v[c].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const unsigned x = xs[q];
+            if (x == (unsigned)kPadId) continue;
+            unsigned s = (x * kMult0) >> SHIFT;
+            for (;;) {
+              const unsigned o = tbl[s];
+              if (o == x) {
+                ++cnt;
+                break;
+              }
+              if (o == kEmpty) break;
+              s = (s + 1) & (TS - 1);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 16; m; m >>= 1) cnt += __shfl_xor_sync(kFull, cnt, m);
+      if (lane == 0) scnt[e] = (unsigned short)cnt;
+    }
+    __syncthreads();
+    // ---- epilogue
+    for (int e = tid; e < k; e += blockDim.x) {
+      const int u = scnt[e];
+      const long long r = (row - row_lo) * (long long)k + e;
+      if (COUNTS_ONLY) {
+        o_u[r] = (CT)u;
+      } else {
+        const bool nz = u > 0;
+        __stcs(o_from + r, nz ? (double)(row + 1) : 0.0);
+        __stcs(o_to + r, nz ? (double)(srow[e] + 1) : 0.0);
+        __stcs(o_w + r, lut[u]);
+      }
+    }
+    __syncthreads();
+  }
+  if (COUNTS_ONLY) __threadfence_system();
+  if (dup) atomicOr(flags, kFlagDupId);
 }
 
 // ---------------------------------------------------------------------------

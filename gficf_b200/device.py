@@ -89,13 +89,14 @@ def jaccard_edges(idx_i32: torch.Tensor, n: int, k: int, row_lo: int = 0, row_hi
 
 def jaccard_counts(idx_i32: torch.Tensor, n: int, k: int, row_lo: int = 0, row_hi: int | None = None,
                    out: torch.Tensor | None = None, flags: torch.Tensor | None = None):
-    """Fast kernel, intersection counts only: uint8 [slab_edges] (k <= 128)."""
+    """Fast kernel, intersection counts only: uint8 [slab_edges] for k <= 255, int16-typed uint16
+    for 255 < k <= 1024."""
     _require_cuda(idx_i32, torch.int32)
     hi = n if row_hi is None else row_hi
     e = (hi - row_lo) * k
     dev = idx_i32.device
     if out is None:
-        out = torch.empty((e,), dtype=torch.uint8, device=dev)
+        out = torch.empty((e,), dtype=torch.uint8 if k <= 255 else torch.int16, device=dev)
     if flags is None:
         flags = new_flags(dev)
     with torch.cuda.device(dev):

@@ -194,8 +194,9 @@ int gficf_cuda_jaccard_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64
                            uint32_t* d_flags, void* stream);
 
 /* Same rows, but only the intersection counts u (one byte per edge when
- * k<=255, layout [(i-row_lo)*k+j]); the compact form that crosses NVLink /
- * feeds gficf_cuda_expand_dev. */
+ * k<=255, two bytes for 255<k<=1024; layout [(i-row_lo)*k+j]); the compact form
+ * that crosses NVLink / feeds gficf_cuda_expand_dev.  GFICF_E_LIMIT for k>1024
+ * (use gficf_cuda_jaccard_exact_dev). */
 int gficf_cuda_jaccard_counts_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
                                   int64_t row_hi, uint8_t* d_u, uint32_t* d_flags, void* stream);
 

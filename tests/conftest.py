@@ -13,6 +13,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_artifacts():
+    """A fresh checkout has no binaries (they are git-ignored): compile the product library and the
+    checkers once per session, exactly what __graft_entry__.build() does."""
+    import gficf_b200
+    from oracle import binding
+
+    if not os.path.exists(gficf_b200.library_path()) or not os.path.exists(binding.ORACLE_SO):
+        sys.path.insert(0, ROOT)
+        import __graft_entry__
+
+        __graft_entry__.build()
+    yield
+
+
 def has_cuda() -> bool:
     try:
         import gficf_b200

@@ -39,15 +39,44 @@ def test_wide_k_kernel(cuda, oracle, k):
     assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(idx), oracle.parallel(idx))
 
 
-@pytest.mark.parametrize("k", [129, 200, 300])
-def test_exact_kernel_large_k(cuda, oracle, k):
+@pytest.mark.parametrize("k", [129, 200, 255, 256, 300, 513, 1000, 1024])
+def test_large_k_kernel(cuda, oracle, k):
+    """128 < k <= 1024: CTA per row, open-addressing table; uint16 counts above 255."""
     rng = np.random.default_rng(k)
-    idx = random_knn(rng, 400, k)
+    idx = random_knn(rng, k + 75, k)
     assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(idx), oracle.parallel(idx))
-    assert np.array_equal(cuda.jaccard_coeff(idx), oracle.serial(idx))
+    if k in (129, 256, 300):
+        assert np.array_equal(cuda.jaccard_coeff(idx), oracle.serial(idx))
 
 
-@pytest.mark.parametrize("n,k", [(500, 8), (300, 30), (200, 64), (150, 100)])
+def test_large_k_device_counts(cuda, oracle):
+    from gficf_b200 import device as D
+
+    n, k = 3000, 400
+    idx0 = synth.knn_index(n, k, family="uniform")
+    padded, flags = D.pad_rows(idx0.cuda())
+    assert padded.shape == (n, 400)
+    cnt, flags = D.jaccard_counts(padded, n, k, flags=flags)
+    assert cnt.dtype == torch.int16 and int(flags[0]) == 0
+    out, _ = D.expand(padded, k, cnt, mode=0)
+    assert np.array_equal(out.cpu().numpy().T, oracle.parallel(synth.to_r_matrix(idx0)))
+    fused, _ = D.jaccard_edges(padded, n, k)
+    assert torch.equal(fused, out)
+
+
+def test_exact_kernel_beyond_fast_range_is_reachable(cuda):
+    """k > 1024 has no fast kernel: the device entry says so, the host entry uses the exact path."""
+    from gficf_b200 import device as D
+
+    n, k = 1100, 1030
+    idx0 = synth.knn_index(n, k, family="uniform")
+    padded, flags = D.pad_rows(idx0.cuda())
+    with pytest.raises(cuda.GficfCudaError) as e:
+        D.jaccard_counts(padded, n, k)
+    assert e.value.code == 5
+
+
+@pytest.mark.parametrize("n,k", [(500, 8), (300, 30), (200, 64), (150, 100), (260, 200)])
 def test_repeated_ids_take_the_exact_path(cuda, oracle, n, k):
     """Rows that list an id twice: multiset semantics in the parallel export
     (std::set_intersection), unique-set semantics in the serial one (Rcpp::intersect)."""
