@@ -410,6 +410,30 @@ def run_ours(a):
             out_sh.close()
             multiproc.comm_destroy()
 
+    # ---- the step after the path, on the device: counts+mutual -> SNN lower triangle
+    snn_rec = None
+    if world == 1 and k <= 127:
+        try:
+            from gficf_b200 import snn
+
+            snn.snn_lower_triangle(padded, n, k)
+            torch.cuda.synchronize()
+            ts = []
+            for i in range(3):
+                flush.fill_(i)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                colptr, srows, sw, sflags = snn.snn_lower_triangle(padded, n, k)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            snn_rec = {"ms": sum(ts) / len(ts), "nnz": int(srows.numel()), "flags": int(sflags[0]),
+                       "what": "count kernel with mutual bit + CSC of the strictly lower triangle of the summed "
+                               "adjacency (replaces the R filter, igraph and the triangle scan), device resident"}
+            del colptr, srows, sw
+        except Exception as ex:  # an extra record, never a reason to lose the bench line
+            snn_rec = {"error": str(ex)[:200]}
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -465,6 +489,8 @@ def run_ours(a):
             "gpu_launches": launches_per_step * a.steps if world == 1 else int(total_launches * a.steps / (a.steps + max(3, a.warmup))),
             "loop_wall_ms": t_wall * 1e3,
         }
+        if snn_rec:
+            line["snn_next_row"] = snn_rec
         if e2e:
             line["e2e"] = e2e
         if cpu:

@@ -53,6 +53,11 @@ PROTOTYPES = {
     "gficf_cuda_expand_dev": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int64, _vp, C.c_int32, _vp, _vp,
                                         _vp, _vp, _vp, _vp]),
     "gficf_cuda_expand_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "gficf_cuda_jaccard_counts_mutual_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _vp,
+                                                       _vp, _vp]),
+    "gficf_cuda_snn_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "gficf_cuda_snn_lower_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp,
+                                           _vp]),
     "gficf_cuda_last_launch": (C.c_int, [C.POINTER(C.c_int32)] * 4),
     "gficf_cuda_version": (C.c_char_p, []),
 }

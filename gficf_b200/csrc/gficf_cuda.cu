@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "jaccard_kernels.cuh"
+#include "snn_kernels.cuh"
 #include "nccl_dyn.h"
 
 namespace {
@@ -125,7 +126,7 @@ int persistent_grid(K kernel, int block, size_t smem, long long work_ctas) {
   return (int)g;
 }
 
-template <int KP, bool CO>
+template <int KP, int CO>
 void launch_small(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
                   uint8_t* u, unsigned* flags, cudaStream_t st) {
   auto kern = jaccard_small_k_kernel<KP, CO>;
@@ -135,7 +136,7 @@ void launch_small(const int* idx, int k, long long lo, long long hi, double* f, 
   tl_launch = {grid, block, (int)(sizeof(unsigned) * kSmallWarps * SmallK<KP>::TS + 33 * 8), KP};
 }
 
-template <int LOG_TS, bool CO>
+template <int LOG_TS, int CO>
 void launch_wide(const int* idx, int k, int kp, long long lo, long long hi, double* f, double* t,
                  double* w, uint8_t* u, unsigned* flags, cudaStream_t st) {
   auto kern = jaccard_wide_k_kernel<LOG_TS, CO>;
@@ -179,11 +180,13 @@ void launch_large(const int* idx, int k, int kp, long long lo, long long hi, dou
   }
 }
 
-// fast kernels; returns false when k is outside their range
-template <bool CO>
+// fast kernels; returns false when k is outside their range.  CO: 0 = (from,to,w) doubles,
+// 1 = counts, 2 = counts with the mutual-neighbour bit (k <= 127)
+template <int CO>
 bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
                  void* u_any, unsigned* flags, cudaStream_t st) {
   uint8_t* u = (uint8_t*)u_any;  // one byte per edge for k <= 255, two above
+  if (CO == 2 && k > 127) return false;  // bit 7 of the count byte carries the mutual flag
   if (hi <= lo) return true;
   const int kp = row_stride(k);
   if (k <= 4) launch_small<4, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
@@ -198,7 +201,8 @@ bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, d
       default: launch_wide<13, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
     }
   } else if (k <= kLargeMaxK) {
-    launch_large<CO>(idx, k, kp, lo, hi, f, t, w, u_any, flags, st);
+    if (CO == 2) return false;
+    launch_large<(CO != 0)>(idx, k, kp, lo, hi, f, t, w, u_any, flags, st);
   } else {
     return false;
   }
@@ -664,7 +668,7 @@ void device_phase1(Slab s, SlabResult* res) {
         if (clo >= chi) break;
         const long long eo = (clo - s.lo) * k;
         CU_TRY(cudaEventRecord(ws.ev_k0[c], ws.s_comp));
-        launch_fast<false>(d_idx, k, clo, chi, d_from + eo, d_to + eo, d_w + eo, nullptr, d_flags,
+        launch_fast<0>(d_idx, k, clo, chi, d_from + eo, d_to + eo, d_w + eo, nullptr, d_flags,
                            ws.s_comp);
         CU_TRY(cudaEventRecord(ws.ev_k1[c], ws.s_comp));
         CU_TRY(cudaEventRecord(ws.ev_chunk[c], ws.s_comp));
@@ -687,7 +691,7 @@ void device_phase1(Slab s, SlabResult* res) {
     } else if (fast_ok && s.slab_e > 0) {
       ws.counts.need(std::max<size_t>(16, (size_t)s.slab_e * cbytes));
       CU_TRY(cudaEventRecord(ws.ev_k0[0], ws.s_comp));
-      launch_fast<true>(d_idx, k, s.lo, s.hi, nullptr, nullptr, nullptr, ws.counts.p, d_flags,
+      launch_fast<1>(d_idx, k, s.lo, s.hi, nullptr, nullptr, nullptr, ws.counts.p, d_flags,
                         ws.s_comp);
       CU_TRY(cudaEventRecord(ws.ev_k1[0], ws.s_comp));
       res->launches++;
@@ -1166,7 +1170,7 @@ int gficf_cuda_jaccard_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64
   DEV_BEGIN
   if (!d_idx_i32 || !d_from || !d_to || !d_w || !d_flags || k < 1 || row_lo < 0 || row_hi > n)
     return GFICF_E_ARG;
-  if (!launch_fast<false>(d_idx_i32, k, row_lo, row_hi, d_from, d_to, d_w, nullptr, d_flags,
+  if (!launch_fast<0>(d_idx_i32, k, row_lo, row_hi, d_from, d_to, d_w, nullptr, d_flags,
                           (cudaStream_t)stream))
     return GFICF_E_LIMIT;
   return GFICF_OK;
@@ -1177,7 +1181,7 @@ int gficf_cuda_jaccard_counts_dev(const int32_t* d_idx_i32, int64_t n, int32_t k
                                   int64_t row_hi, uint8_t* d_u, uint32_t* d_flags, void* stream) {
   DEV_BEGIN
   if (!d_idx_i32 || !d_u || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
-  if (!launch_fast<true>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u, d_flags,
+  if (!launch_fast<1>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u, d_flags,
                          (cudaStream_t)stream))
     return GFICF_E_LIMIT;
   return GFICF_OK;
@@ -1207,6 +1211,62 @@ int gficf_cuda_expand_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, i
   if (mode != GFICF_MODE_SERIAL && mode != GFICF_MODE_PARALLEL) return GFICF_E_ARG;
   launch_expand(d_idx_i32, k, row_lo, row_hi, d_u, mode, d_from, d_to, d_w, d_scratch,
                 (long long*)d_n_written, (cudaStream_t)stream);
+  return GFICF_OK;
+  DEV_END
+}
+
+// ---------------------------------------------------------------- SNN graph (next row after the path)
+int gficf_cuda_jaccard_counts_mutual_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                                         int64_t row_hi, uint8_t* d_um, uint32_t* d_flags, void* stream) {
+  DEV_BEGIN
+  if (!d_idx_i32 || !d_um || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
+  if (!launch_fast<2>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_um, d_flags,
+                      (cudaStream_t)stream))
+    return GFICF_E_LIMIT;
+  return GFICF_OK;
+  DEV_END
+}
+
+size_t gficf_cuda_snn_scratch_bytes(int64_t n, int64_t cap) {
+  if (n < 0 || cap < 0) return 0;
+  const size_t nb = (size_t)((n + kScanBlock - 1) / kScanBlock + 2);
+  // counts[n] | cursor[n] | block sums | total | col_tmp[cap] | row_tmp[cap] | w_tmp[cap]
+  return (size_t)n * 8 + nb * 8 + 64 + (size_t)cap * 16 + 256;
+}
+
+int gficf_cuda_snn_lower_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, const uint8_t* d_um,
+                             int64_t* d_colptr, int32_t* d_row, double* d_w, int64_t cap,
+                             void* d_scratch, uint32_t* d_flags, void* stream) {
+  DEV_BEGIN
+  if (!d_idx_i32 || !d_um || !d_colptr || !d_row || !d_w || !d_scratch || !d_flags || n < 1 || k < 1)
+    return GFICF_E_ARG;
+  if (k > 127 || n >= 0x7fffffffLL) return GFICF_E_LIMIT;
+  if (cap < n * (int64_t)k) return GFICF_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kp = row_stride(k);
+  const long long nb = (n + kScanBlock - 1) / kScanBlock;
+  char* sc = (char*)d_scratch;
+  int* cnt = (int*)sc;
+  int* cursor = cnt + n;
+  long long* block_sums = (long long*)(sc + (((size_t)n * 8 + 63) / 64) * 64);
+  long long* total = block_sums + nb + 1;
+  char* tmp = (char*)(total + 1);
+  tmp = (char*)((((uintptr_t)tmp + 63) / 64) * 64);
+  double* w_tmp = (double*)tmp;
+  int* col_tmp = (int*)(w_tmp + cap);
+  int* row_tmp = col_tmp + cap;
+  CU_TRY(cudaMemsetAsync(cnt, 0, (size_t)n * 8, st));  // counts and cursors
+  const int grid = grid_1d(n * 32, 256, 8);
+  snn_edges_kernel<false><<<grid, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, cnt, nullptr, nullptr, nullptr,
+                                               nullptr, d_flags);
+  scan_block_sums_kernel<<<(int)nb, kScanBlock, 0, st>>>(cnt, n, block_sums);
+  compact_scan_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
+  scan_finish_kernel<<<(int)nb, kScanBlock, 0, st>>>(cnt, n, block_sums, total, (long long*)d_colptr);
+  snn_edges_kernel<true><<<grid, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, cursor, (const long long*)d_colptr,
+                                              col_tmp, row_tmp, w_tmp, d_flags);
+  snn_rank_sort_kernel<<<grid_1d(n * (long long)k, 256, 8), 256, 0, st>>>(
+      (const long long*)d_colptr, total, col_tmp, row_tmp, w_tmp, d_row, d_w);
+  CU_TRY(cudaGetLastError());
   return GFICF_OK;
   DEV_END
 }

@@ -95,8 +95,9 @@ __device__ __forceinline__ unsigned slot_addr(unsigned tbl32, unsigned x, unsign
 
 // membership probes of the 4 ids of one 16-byte piece against a collision-free table at
 // shared address tbl32: per id IMAD (hash), SHF (slot), LEA (address), LDS, ISETP, @p IADD
-template <unsigned INC, int SHIFT>
-__device__ __forceinline__ void probe4(unsigned& acc, unsigned tbl32, unsigned mult, const int4& v) {
+template <unsigned INC, int SHIFT, bool MUT = false>
+__device__ __forceinline__ void probe4(unsigned& acc, unsigned tbl32, unsigned mult, const int4& v,
+                                       unsigned self = 0) {
   const unsigned x0 = (unsigned)v.x, x1 = (unsigned)v.y, x2 = (unsigned)v.z, x3 = (unsigned)v.w;
   const unsigned k0 = lds_u32(slot_addr<SHIFT>(tbl32, x0, mult));
   const unsigned k1 = lds_u32(slot_addr<SHIFT>(tbl32, x1, mult));
@@ -106,6 +107,12 @@ __device__ __forceinline__ void probe4(unsigned& acc, unsigned tbl32, unsigned m
   add_if_eq<INC>(acc, k1, x1);
   add_if_eq<INC>(acc, k2, x2);
   add_if_eq<INC>(acc, k3, x3);
+  if (MUT) {  // bit 7 of the edge's byte: the neighbour's own list contains this row (i in N(t))
+    add_if_eq<INC * 0x80u>(acc, x0, self);
+    add_if_eq<INC * 0x80u>(acc, x1, self);
+    add_if_eq<INC * 0x80u>(acc, x2, self);
+    add_if_eq<INC * 0x80u>(acc, x3, self);
+  }
 }
 
 __device__ __forceinline__ double jaccard_weight(int u, int k) {
@@ -207,12 +214,15 @@ struct SmallK {
 
 constexpr int kSmallWarps = GFICF_SMALL_WARPS;
 
-template <int KP, bool COUNTS_ONLY>
+// OUT: 0 = (from,to,w) doubles, 1 = counts, 2 = counts with the mutual-neighbour bit (bit 7)
+template <int KP, int OUT>
 __global__ void __launch_bounds__(kSmallWarps * 32, GFICF_SMALL_MINB)
 jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, long long row_hi,
                        double* __restrict__ o_from, double* __restrict__ o_to,
                        double* __restrict__ o_w, uint8_t* __restrict__ o_u,
                        unsigned* __restrict__ flags) {
+  constexpr bool COUNTS_ONLY = OUT != 0;
+  constexpr bool MUT = OUT == 2;
   using G = SmallK<KP>;
   constexpr int LPE = G::LPE, S = G::S, TS = G::TS, SHIFT = 32 - G::LOG_TS;
   __shared__ unsigned tbl_all[kSmallWarps][TS];
@@ -304,10 +314,10 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     const unsigned tbl32 = smem_addr(tbl);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      if ((s & 3) == 0) probe4<1u, SHIFT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s]);
-      if ((s & 3) == 1) probe4<1u << 8, SHIFT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s]);
-      if ((s & 3) == 2) probe4<1u << 16, SHIFT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s]);
-      if ((s & 3) == 3) probe4<1u << 24, SHIFT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s]);
+      if ((s & 3) == 0) probe4<1u, SHIFT, MUT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s], (unsigned)row);
+      if ((s & 3) == 1) probe4<1u << 8, SHIFT, MUT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s], (unsigned)row);
+      if ((s & 3) == 2) probe4<1u << 16, SHIFT, MUT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s], (unsigned)row);
+      if ((s & 3) == 3) probe4<1u << 24, SHIFT, MUT>(s < 4 ? c_lo : c_hi, tbl32, mult, v[s], (unsigned)row);
     }
 #pragma unroll
     for (int m = 1; m < LPE; m <<= 1) {
@@ -373,15 +383,15 @@ __device__ __forceinline__ void wide_load(int4 (&v)[kWideU], const char* lane_ba
   }
 }
 
-template <int N, int SHIFT>
+template <int N, int SHIFT, bool MUT>
 __device__ __forceinline__ void wide_probe(const int4 (&v)[kWideU], unsigned tbl, unsigned mult,
-                                           unsigned& a0, unsigned& a1) {
+                                           unsigned& a0, unsigned& a1, unsigned self) {
 #pragma unroll
   for (int q = 0; q < N; ++q) {
-    if ((q & 3) == 0) probe4<1u, SHIFT>(q < 4 ? a0 : a1, tbl, mult, v[q]);
-    if ((q & 3) == 1) probe4<1u << 8, SHIFT>(q < 4 ? a0 : a1, tbl, mult, v[q]);
-    if ((q & 3) == 2) probe4<1u << 16, SHIFT>(q < 4 ? a0 : a1, tbl, mult, v[q]);
-    if ((q & 3) == 3) probe4<1u << 24, SHIFT>(q < 4 ? a0 : a1, tbl, mult, v[q]);
+    if ((q & 3) == 0) probe4<1u, SHIFT, MUT>(q < 4 ? a0 : a1, tbl, mult, v[q], self);
+    if ((q & 3) == 1) probe4<1u << 8, SHIFT, MUT>(q < 4 ? a0 : a1, tbl, mult, v[q], self);
+    if ((q & 3) == 2) probe4<1u << 16, SHIFT, MUT>(q < 4 ? a0 : a1, tbl, mult, v[q], self);
+    if ((q & 3) == 3) probe4<1u << 24, SHIFT, MUT>(q < 4 ? a0 : a1, tbl, mult, v[q], self);
   }
 }
 
@@ -398,13 +408,15 @@ __device__ __forceinline__ void wide_probe(const int4 (&v)[kWideU], unsigned tbl
     default: break;                    \
   }
 
-template <int LOG_TS, bool COUNTS_ONLY>
+template <int LOG_TS, int OUT>
 __global__ void __launch_bounds__(kWideWarps * 32, GFICF_WIDE_MINB)
 jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo,
                       long long row_hi, double* __restrict__ o_from, double* __restrict__ o_to,
                       double* __restrict__ o_w, uint8_t* __restrict__ o_u,
                       unsigned* __restrict__ flags) {
   constexpr int TS = 1 << LOG_TS, SHIFT = 32 - LOG_TS;
+  constexpr bool COUNTS_ONLY = OUT != 0;
+  constexpr bool MUT = OUT == 2;  // needs k <= 127 (bit 7 of the count byte)
   extern __shared__ unsigned smem_u[];
   unsigned* tbl = smem_u;                             // [TS]
   int* srow_base = reinterpret_cast<int*>(tbl + TS);   // [2][128] ids of row i
@@ -507,7 +519,7 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
       unsigned acc[kWideU / 4];
 #pragma unroll
       for (int q = 0; q < kWideU / 4; ++q) acc[q] = 0;
-      GFICF_WIDE_DISPATCH(cnt, (wide_probe<N, SHIFT>(v, tbl32, mult, acc[0], acc[1])))
+      GFICF_WIDE_DISPATCH(cnt, (wide_probe<N, SHIFT, MUT>(v, tbl32, mult, acc[0], acc[1], (unsigned)row)))
       // next batch's gathers fly while this batch's counts are reduced
       if (b + 1 < nb) {
         const int n0 = e0 + bsz;

@@ -223,6 +223,23 @@ int gficf_cuda_expand_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, i
                           void* d_scratch, int64_t* d_n_written, void* stream);
 size_t gficf_cuda_expand_scratch_bytes(int64_t slab_edges);
 
+/* ---- the step after the path: counts -> the graph the community detection
+ * reads.  Replaces, on the device, relations[relations[,3]>0,] + igraph::graph.data.frame +
+ * as_adjacency_matrix (parallel edges summed) of R/clustCells.R:66-69,81 and the strictly-lower-
+ * triangle scan of src/RModularityOptimizer.cpp:67-83. ---- */
+#define GFICF_FLAG_ISOLATED 16u /* some cell has no edge with u>0: igraph would number vertices differently */
+/* Count kernel that also sets bit 7 of an edge's byte when the edge is mutual (i is in N(t)); k <= 127. */
+int gficf_cuda_jaccard_counts_mutual_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                                         int64_t row_hi, uint8_t* d_um, uint32_t* d_flags, void* stream);
+/* CSC of the strictly lower triangle of the symmetric weighted adjacency matrix: d_colptr[n+1]
+ * (int64), d_row / d_w with capacity cap >= n*k entries, rows ascending inside a column
+ * (column = node1, row = node2 of the reference's edge list).  d_um covers all n rows.
+ * Valid when *d_flags stays free of GFICF_FLAG_DUP_ID / _HASH_FAIL / _ISOLATED. */
+size_t gficf_cuda_snn_scratch_bytes(int64_t n, int64_t cap);
+int gficf_cuda_snn_lower_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, const uint8_t* d_um,
+                             int64_t* d_colptr, int32_t* d_row, double* d_w, int64_t cap,
+                             void* d_scratch, uint32_t* d_flags, void* stream);
+
 /* Launch geometry of the last fast-kernel launch on this thread (for the
  * bench record): grid, block, dynamic smem bytes, kernels launched. */
 int gficf_cuda_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* variant);
