@@ -375,15 +375,27 @@ def run_ours(a):
             multiproc.comm_init_from_torch()
             tag = [("gficf_bench_%d_%d" % (os.getpid(), int(time.time()))) if rank == 0 else None]
             dist.broadcast_object_list(tag, src=0)
+            # NUMA: every rank runs on the CPUs next to its GPU and first-touches the rows it will
+            # move, so the D2H streams of 8 GPUs do not all land on one socket's memory
+            numa = multiproc.bind_to_gpu_numa_node(local)
             r_sh = out_sh = None
             if rank == 0:
-                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=True)
-                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=True)
-                r_sh.array[...] = synth.to_r_matrix(idx0)
+                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=True, pin=False)
+                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=True, pin=False)
             dist.barrier()
             if rank != 0:
-                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=False)
-                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=False)
+                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=False, pin=False)
+                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=False, pin=False)
+            s_lo, s_hi = sharding.slab_bounds(n, world, rank)
+            r_sh.first_touch_rows(s_lo, s_hi)
+            out_sh.first_touch_rows(s_lo * k, s_hi * k)
+            dist.barrier()
+            if rank == 0:
+                r_sh.array[...] = synth.to_r_matrix(idx0)
+            dist.barrier()
+            r_sh.pin()
+            out_sh.pin()
+            dist.barrier()
             for _ in range(2):
                 multiproc.rcpp_parallel_jaccard_coef_rank(r_sh.array, out_sh.array)
             barrier()
@@ -397,7 +409,7 @@ def run_ours(a):
                    "d2h_bytes_per_step": 24 * E, "ms_per_step": float(dt[0]) * 1e3,
                    "call": "gficf_b200.multiproc.rcpp_parallel_jaccard_coef_rank (one rank per GPU, shared "
                            "page-locked host matrices; each rank moves its own row slab)",
-                   "pinned": bool(r_sh.pinned and out_sh.pinned),
+                   "pinned": bool(r_sh.pinned and out_sh.pinned), "numa_binding_rank0": numa,
                    "breakdown_ms_rank0": {kk: round(v, 3) for kk, v in gficf_b200.last_timings().items()
                                           if kk != "reserved"}}
             if rank == 0:

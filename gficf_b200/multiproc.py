@@ -45,8 +45,37 @@ def comm_destroy() -> None:
     _lib.lib().gficf_cuda_comm_destroy()
 
 
+def bind_to_gpu_numa_node(device_index: int) -> str:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (so that the pages it
+    first-touches and its staging threads are local to the GPU's PCIe root).  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return "node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:  # containers without sysfs / nvml: run unbound
+        return "unbound (%s)" % type(e).__name__
+
+
 class SharedHostMatrix:
-    """A Fortran-ordered float64 matrix in /dev/shm, mapped by every rank and page-locked."""
+    """A Fortran-ordered float64 matrix in /dev/shm, mapped by every rank and page-locked.
+
+    Two-step use when NUMA placement matters: construct with pin=False on every rank, let each rank
+    `first_touch_rows()` the rows it will move (the pages then live on that rank's NUMA node),
+    barrier, then `pin()`."""
 
     def __init__(self, name: str, shape, create: bool, pin: bool = True):
         self.path = os.path.join("/dev/shm", name)
@@ -56,9 +85,19 @@ class SharedHostMatrix:
         self.mm = np.memmap(self.path, dtype=np.float64, mode="w+" if create else "r+", shape=(max(n, 1),))
         self.array = self.mm[:n].reshape(self.shape, order="F")
         self.pinned = False
-        if pin and n:
-            rc = _lib.lib().gficf_cuda_host_register(self.mm.ctypes.data, n * 8)
-            self.pinned = rc == 0
+        if pin:
+            self.pin()
+
+    def pin(self) -> bool:
+        n = int(np.prod(self.shape))
+        if n and not self.pinned:
+            self.pinned = _lib.lib().gficf_cuda_host_register(self.mm.ctypes.data, n * 8) == 0
+        return self.pinned
+
+    def first_touch_rows(self, lo: int, hi: int) -> None:
+        """Write zeros to rows [lo,hi) of every column (allocates those pages on the caller's node)."""
+        if hi > lo:
+            self.array[lo:hi, :] = 0.0
 
     def close(self):
         if self.pinned:
