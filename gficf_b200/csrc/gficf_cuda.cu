@@ -126,14 +126,23 @@ int persistent_grid(K kernel, int block, size_t smem, long long work_ctas) {
   return (int)g;
 }
 
-template <int KP, int CO>
-void launch_small(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
-                  uint8_t* u, unsigned* flags, cudaStream_t st) {
-  auto kern = jaccard_small_k_kernel<KP, CO>;
+template <int KP, int CO, bool SKIP>
+void launch_small_t(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
+                    uint8_t* u, unsigned* flags, cudaStream_t st) {
+  auto kern = jaccard_small_k_kernel<KP, CO, SKIP>;
   const int block = kSmallWarps * 32;
   const int grid = persistent_grid(kern, block, 0, (hi - lo + kSmallWarps - 1) / kSmallWarps);
   kern<<<grid, block, 0, st>>>(idx, k, lo, hi, f, t, w, u, flags);
   tl_launch = {grid, block, (int)(sizeof(unsigned) * kSmallWarps * SmallK<KP>::TS + 33 * 8), KP};
+}
+
+// the pad-skipping variant costs registers, so it is used only when a whole 16-byte piece of every
+// row is padding (k <= KP-4, e.g. k=25..28 in 32-int rows); k=30 keeps the lean variant
+template <int KP, int CO>
+void launch_small(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
+                  uint8_t* u, unsigned* flags, cudaStream_t st) {
+  if (KP > 4 && k <= KP - 4) launch_small_t<KP, CO, true>(idx, k, lo, hi, f, t, w, u, flags, st);
+  else launch_small_t<KP, CO, false>(idx, k, lo, hi, f, t, w, u, flags, st);
 }
 
 template <int LOG_TS, int CO>
@@ -322,6 +331,7 @@ struct PinBuf {
 constexpr int kMaxChunks = 32;
 constexpr size_t kStageChunk = 4u << 20;  // pageable host memory moves in pieces of this size
 constexpr int kStageSlots = 16;           // through a ring of pinned slots (64 MiB per device)
+constexpr size_t kSmallCopyBytes = 8u << 20;  // below this, pageable copies go through the driver's own staging
 
 struct DeviceWs {
   int dev = -1;
@@ -548,6 +558,12 @@ void h2d_block(DeviceWs& ws, const double* src, long long ld_src, double* dst, l
                              rows * sizeof(double), cols, cudaMemcpyHostToDevice, st));
     return;
   }
+  if ((size_t)rows * cols * sizeof(double) <= kSmallCopyBytes) {
+    // small matrices: the driver's own staging is faster than spinning up the copy threads
+    CU_TRY(cudaMemcpy2DAsync(dst, rows * sizeof(double), src, ld_src * sizeof(double),
+                             rows * sizeof(double), cols, cudaMemcpyHostToDevice, st));
+    return;
+  }
   std::vector<Seg> segs;
   for (int c = 0; c < cols; ++c)
     segs.push_back({(char*)(src + (long long)c * ld_src), (char*)(dst + (long long)c * rows),
@@ -559,7 +575,9 @@ void h2d_block(DeviceWs& ws, const double* src, long long ld_src, double* dst, l
 // plain async copies; pageable ones: staged_copy.
 void d2h_segs(DeviceWs& ws, const std::vector<Seg>& segs, cudaStream_t st) {
   if (segs.empty()) return;
-  if (is_pinned(segs[0].host)) {
+  size_t total = 0;
+  for (const Seg& g : segs) total += g.bytes;
+  if (is_pinned(segs[0].host) || total <= kSmallCopyBytes) {
     for (const Seg& g : segs) {
       if (g.wait_before) CU_TRY(cudaStreamWaitEvent(st, g.wait_before, 0));
       if (g.bytes) CU_TRY(cudaMemcpyAsync(g.host, g.dev, g.bytes, cudaMemcpyDeviceToHost, st));

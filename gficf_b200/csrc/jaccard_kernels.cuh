@@ -215,7 +215,7 @@ struct SmallK {
 constexpr int kSmallWarps = GFICF_SMALL_WARPS;
 
 // OUT: 0 = (from,to,w) doubles, 1 = counts, 2 = counts with the mutual-neighbour bit (bit 7)
-template <int KP, int OUT>
+template <int KP, int OUT, bool SKIP>
 __global__ void __launch_bounds__(kSmallWarps * 32, GFICF_SMALL_MINB)
 jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, long long row_hi,
                        double* __restrict__ o_from, double* __restrict__ o_to,
@@ -239,6 +239,8 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
   long long row = row_lo + (long long)blockIdx.x * kSmallWarps + warp;
   // which 16-byte piece of a neighbour row this lane fetches
   const char* lane_base = reinterpret_cast<const char*>(idx + (lane % LPE) * 4);
+  // SKIP (chosen by the host when k <= KP-4): a 16-byte piece that holds only pads is never fetched
+  const bool piece_on = !SKIP || (lane % LPE) * 4 < k;
   const int grp = lane / LPE;
   const bool valid = lane < k;
   unsigned warp_flags = 0;
@@ -256,8 +258,8 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     for (int s = 0; s < S; ++s) {
       const int e = grp * S + s;
       const int t = __shfl_sync(kFull, a, e & 31);
-      v[s] = (e < k) ? ldg_row(lane_base, (unsigned)t, KP * 4)
-                     : make_int4(kPadId, kPadId, kPadId, kPadId);
+      v[s] = (e < k && piece_on) ? ldg_row(lane_base, (unsigned)t, KP * 4)
+                                 : make_int4(kPadId, kPadId, kPadId, kPadId);
     }
     // ---- collision-free hash of N(i): search a multiplier
     unsigned mult = kMult0, slot;
@@ -430,7 +432,7 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
   __syncthreads();
 
   const int c0 = lane * 4;
-  const bool lane_on = c0 < kp;
+  const bool lane_on = c0 < k;  // lanes whose 16-byte piece holds only pads never load (nor probe)
   const char* lane_base = reinterpret_cast<const char*>(idx + c0);
   const unsigned row_bytes = (unsigned)kp * 4u;
   // gathered pieces; lanes past the end of a row never load and keep these pads for good

@@ -13,8 +13,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 cat gpurun_out/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?" | tee -a gpurun_out/summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:jaccard_small_k -s 3 -c 1 -o gpurun_out/prof_small_k_final -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" | tee -a gpurun_out/summary.txt
-timeout 900 python bench.py --cells 1000000 --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_1m.json 2>/dev/null; cat gpurun_out/bench_1m.json
-timeout 900 python bench.py --cells 10000000 --k 100 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_cfg5_n1.json 2>/dev/null; cat gpurun_out/bench_cfg5_n1.json
+timeout 1500 python tools/all_configs.py > gpurun_out/all_configs.md 2> gpurun_out/all_configs.err; cat gpurun_out/all_configs.md
 fi
 if [ "$1" = "full" ]; then
 # race / memory checks of the hand-written kernels on small inputs (shared-memory hash tables, warp-synchronous code)
