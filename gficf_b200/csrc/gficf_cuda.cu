@@ -1248,7 +1248,7 @@ int gficf_cuda_jaccard_counts_mutual_dev(const int32_t* d_idx_i32, int64_t n, in
 size_t gficf_cuda_snn_scratch_bytes(int64_t n, int64_t cap) {
   if (n < 0 || cap < 0) return 0;
   const size_t nb = (size_t)((n + kScanBlock - 1) / kScanBlock + 2);
-  // counts[n] | cursor[n] | block sums | total | col_tmp[cap] | row_tmp[cap] | w_tmp[cap]
+  // counts[n] | cursor[n] | block sums | total | staged entries[cap] (16 B each)
   return (size_t)n * 8 + nb * 8 + 64 + (size_t)cap * 16 + 256;
 }
 
@@ -1270,20 +1270,17 @@ int gficf_cuda_snn_lower_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, con
   long long* total = block_sums + nb + 1;
   char* tmp = (char*)(total + 1);
   tmp = (char*)((((uintptr_t)tmp + 63) / 64) * 64);
-  double* w_tmp = (double*)tmp;
-  int* col_tmp = (int*)(w_tmp + cap);
-  int* row_tmp = col_tmp + cap;
+  SnnEntry* entries = (SnnEntry*)tmp;  // [cap]
   CU_TRY(cudaMemsetAsync(cnt, 0, (size_t)n * 8, st));  // counts and cursors
   const int grid = grid_1d(n * 32, 256, 8);
-  snn_edges_kernel<false><<<grid, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, cnt, nullptr, nullptr, nullptr,
-                                               nullptr, d_flags);
+  snn_edges_kernel<false><<<grid, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, cnt, nullptr, nullptr, d_flags);
   scan_block_sums_kernel<<<(int)nb, kScanBlock, 0, st>>>(cnt, n, block_sums);
   compact_scan_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
   scan_finish_kernel<<<(int)nb, kScanBlock, 0, st>>>(cnt, n, block_sums, total, (long long*)d_colptr);
   snn_edges_kernel<true><<<grid, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, cursor, (const long long*)d_colptr,
-                                              col_tmp, row_tmp, w_tmp, d_flags);
+                                              entries, d_flags);
   snn_rank_sort_kernel<<<grid_1d(n * (long long)k, 256, 8), 256, 0, st>>>(
-      (const long long*)d_colptr, total, col_tmp, row_tmp, w_tmp, d_row, d_w);
+      (const long long*)d_colptr, total, entries, d_row, d_w);
   CU_TRY(cudaGetLastError());
   return GFICF_OK;
   DEV_END

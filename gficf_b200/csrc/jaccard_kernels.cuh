@@ -308,6 +308,7 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
       mult = next_mult(mult);
     }
 #endif
+    __syncwarp();  // every lane has read its slot's owner before the keys overwrite the lane ids
     if (valid) tbl[slot] = (unsigned)a;
     if (__any_sync(kFull, dup)) warp_flags |= kFlagDupId;
     __syncwarp();

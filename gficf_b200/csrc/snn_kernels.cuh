@@ -23,13 +23,19 @@ namespace gficf {
 
 constexpr unsigned kFlagIsolated = 16u;  // some cell has no edge with u>0: vertex numbering differs
 
+// one staged entry of pass 2: a single 16-byte store per entry (the scattered ones land at random
+// positions, three separate 4/4/8-byte stores tripled the partial-sector writes)
+struct __align__(16) SnnEntry {
+  int col, row;
+  double w;
+};
+
 // pass 1 (count) / pass 2 (scatter): one warp per row
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
 snn_edges_kernel(const int* __restrict__ idx, const uint8_t* __restrict__ um, long long n, int k, int kp,
                  int* __restrict__ cnt_or_cursor, const long long* __restrict__ colptr,
-                 int* __restrict__ col_tmp, int* __restrict__ row_tmp, double* __restrict__ w_tmp,
-                 unsigned* __restrict__ flags) {
+                 SnnEntry* __restrict__ tmp, unsigned* __restrict__ flags) {
   __shared__ double lut[128];
   if ((int)threadIdx.x <= k && threadIdx.x < 128) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
   __syncthreads();
@@ -74,9 +80,11 @@ snn_edges_kernel(const int* __restrict__ idx, const uint8_t* __restrict__ um, lo
         }
         if (pos >= 0) {
           const double w = lut[u];
-          col_tmp[pos] = col;
-          row_tmp[pos] = row;
-          w_tmp[pos] = mut ? w + w : w;  // both directions present: the two equal weights summed
+          SnnEntry en;
+          en.col = col;
+          en.row = row;
+          en.w = mut ? w + w : w;  // both directions present: the two equal weights summed
+          tmp[pos] = en;
         }
       }
     }
@@ -136,19 +144,17 @@ scan_finish_kernel(const int* __restrict__ cnt, long long n, const long long* __
 // warp mostly share a column, so the scans are broadcast reads.
 __global__ void __launch_bounds__(256)
 snn_rank_sort_kernel(const long long* __restrict__ colptr, const long long* __restrict__ nnz,
-                     const int* __restrict__ col_tmp, const int* __restrict__ row_tmp,
-                     const double* __restrict__ w_tmp, int* __restrict__ row_out,
+                     const SnnEntry* __restrict__ tmp, int* __restrict__ row_out,
                      double* __restrict__ w_out) {
   const long long total = *nnz;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
        p += (long long)gridDim.x * blockDim.x) {
-    const int c = col_tmp[p];
-    const int r = row_tmp[p];
-    const long long lo = colptr[c], hi = colptr[c + 1];
+    const SnnEntry en = tmp[p];
+    const long long lo = colptr[en.col], hi = colptr[en.col + 1];
     int rank = 0;
-    for (long long q = lo; q < hi; ++q) rank += row_tmp[q] < r;
-    row_out[lo + rank] = r;
-    w_out[lo + rank] = w_tmp[p];
+    for (long long q = lo; q < hi; ++q) rank += tmp[q].row < en.row;
+    row_out[lo + rank] = en.row;
+    w_out[lo + rank] = en.w;
   }
 }
 
