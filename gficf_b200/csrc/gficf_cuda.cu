@@ -8,6 +8,9 @@
 #include "../../include/gficf_cuda.h"
 
 #include <cuda_runtime.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -447,14 +450,49 @@ int copy_threads() {
     const char* e = getenv("GFICF_CUDA_COPY_THREADS");
     int v = e ? atoi(e) : 0;
     if (v <= 0) {
-      // measured on a 16-thread host (4M x 30, pageable in/out): 2 threads 248 ms, 4: 137, 8: 94,
-      // 12: 90, 16: 111 (pinned buffers: 72 ms)
+      // measured on a 16-thread host (4M x 30, pageable in/out, non-temporal copy-out): 2 threads
+      // 183 ms, 4: 79, 6: 74, 8: 74, 12: 76, 16: 100 (pinned buffers: 72 ms)
       v = (int)std::thread::hardware_concurrency() / 2;
-      v = std::max(2, std::min(12, v));
+      v = std::max(2, std::min(8, v));
     }
     return v;
   }();
   return std::max(2, t / std::max(1, g_active_devices.load()));
+}
+
+// Device -> pageable host: the destination will not be read again soon, so the pieces are written
+// with non-temporal stores (no read-for-ownership of the destination lines).
+void copy_out(char* dst, const char* src, size_t bytes) {
+#if defined(__x86_64__) && defined(__SSE2__)
+  if (bytes >= 4096 && (((uintptr_t)dst ^ (uintptr_t)src) & 7) == 0) {
+    while (((uintptr_t)dst & 15) && bytes >= 8) {
+      memcpy(dst, src, 8);
+      dst += 8;
+      src += 8;
+      bytes -= 8;
+    }
+    if (((uintptr_t)dst & 15) == 0) {
+      const size_t blocks = bytes / 64;
+      const __m128i* s = (const __m128i*)src;
+      __m128i* d = (__m128i*)dst;
+      for (size_t b = 0; b < blocks; ++b) {
+        const __m128i x0 = _mm_loadu_si128(s + 0), x1 = _mm_loadu_si128(s + 1);
+        const __m128i x2 = _mm_loadu_si128(s + 2), x3 = _mm_loadu_si128(s + 3);
+        _mm_stream_si128(d + 0, x0);
+        _mm_stream_si128(d + 1, x1);
+        _mm_stream_si128(d + 2, x2);
+        _mm_stream_si128(d + 3, x3);
+        s += 4;
+        d += 4;
+      }
+      _mm_sfence();
+      dst += blocks * 64;
+      src += blocks * 64;
+      bytes -= blocks * 64;
+    }
+  }
+#endif
+  if (bytes) memcpy(dst, src, bytes);
 }
 
 struct Piece {
@@ -511,7 +549,7 @@ void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cud
           std::this_thread::yield();
         }
         if (cudaEventSynchronize(ws.ev_slot[j % kStageSlots]) != cudaSuccess) failed.store(true);
-        memcpy(pc.host, slot, pc.bytes);
+        copy_out(pc.host, slot, pc.bytes);
         host_done[j].store(1, std::memory_order_release);
       }
     }
