@@ -254,7 +254,12 @@ def run_ours(a):
         out = torch.empty((3, E), dtype=torch.float64, device=dev) if rank == 0 else None
         counts_all = torch.empty(E, dtype=torch.uint8, device=dev)
         if a.gather == "peer":
-            pg = sharding.PeerGather(n, k, rho=rho, chunks=4)
+            try:
+                pg = sharding.PeerGather(n, k, rho=rho, chunks=4)
+            except RuntimeError as ex:  # raised on every rank together
+                sys.stderr.write("bench.py: %s; falling back to NCCL send/recv\n" % ex)
+                a.gather = "nccl"
+        if a.gather == "peer":
 
             def step():
                 pg.step(padded, out)

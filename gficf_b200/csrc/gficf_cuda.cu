@@ -682,7 +682,10 @@ void d2h_slab(DeviceWs& ws, const Slab& s, SlabResult* res) {
 //   parallel export, k<=128: fused kernel in row chunks, the D2H of chunk c overlapping the
 //     kernel of chunk c+1 (the result stands unless some device raises a dup/hash flag);
 //   serial export, k<=128:   fast count kernel (the compaction happens in phase 2).
-void device_phase1(Slab s, SlabResult* res) {
+// Phase 0: everything that can fail locally -- workspaces, H2D of the device's rows, layout
+// pre-pass.  No collective in here: if any device fails, the call ends before anybody enters the
+// all-gather (a collective that one participant never joins would hang the others' GPUs).
+void device_phase0(Slab s, SlabResult* res) {
   try {
     DeviceWs& ws = g_ws[s.dev];
     CU_TRY(cudaSetDevice(s.dev));
@@ -692,9 +695,12 @@ void device_phase1(Slab s, SlabResult* res) {
     ws.in_f64.need(std::max<size_t>(16, (size_t)s.rows * k * sizeof(double)));
     ws.idx.need(std::max<size_t>(16, (size_t)s.rows_per * s.ndev * s.kp * sizeof(int)));
     ws.out.need(std::max<size_t>(16, (size_t)s.slab_e * 3 * sizeof(double)));
+    if (s.mode == GFICF_MODE_SERIAL || k > kLargeMaxK) {
+      ws.counts.need(std::max<size_t>(16, (size_t)s.slab_e * cbytes));
+      ws.scratch.need(expand_scratch_bytes(s.slab_e));
+    }
     unsigned* d_flags = (unsigned*)ws.small.p;
     CU_TRY(cudaMemsetAsync(ws.small.p, 0, 64, ws.s_comp));
-
     CU_TRY(cudaEventRecord(ws.ev[0], ws.s_comp));
     h2d_block(ws, s.h_idx + s.lo, s.n, (double*)ws.in_f64.p, s.rows, k, ws.s_comp);
     CU_TRY(cudaEventRecord(ws.ev[1], ws.s_comp));
@@ -702,6 +708,18 @@ void device_phase1(Slab s, SlabResult* res) {
                   ws.s_comp);
     res->launches += s.rows > 0;
     CU_TRY(cudaEventRecord(ws.ev[2], ws.s_comp));
+  } catch (const Err& e) {
+    res->err = e;
+  }
+}
+
+void device_phase1(Slab s, SlabResult* res) {
+  try {
+    DeviceWs& ws = g_ws[s.dev];
+    CU_TRY(cudaSetDevice(s.dev));
+    const int k = s.k;
+    const int cbytes = k <= 255 ? 1 : 2;
+    unsigned* d_flags = (unsigned*)ws.small.p;
     if (s.ndev > 1) {
       const size_t cnt = (size_t)s.rows_per * s.kp;
       NCCL_TRY(nccl_dyn::get().AllGather((const char*)ws.idx.p + (size_t)s.rank * cnt * sizeof(int),
@@ -957,10 +975,18 @@ int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int
       if (r.err.code != GFICF_OK) throw r.err;
   };
   if (ndev == 1) {
+    device_phase0(slabs[0], &res[0]);
+    first_error();
     device_phase1(slabs[0], &res[0]);
   } else {
     nccl_ensure(ndev);
     for (int r = 0; r < ndev; ++r) slabs[r].comm = g_nccl.comms[r];
+    {
+      std::vector<std::thread> th;
+      for (int r = 0; r < ndev; ++r) th.emplace_back(device_phase0, slabs[r], &res[r]);
+      for (auto& t : th) t.join();
+    }
+    first_error();  // nobody has entered a collective yet
     std::vector<std::thread> th;
     for (int r = 0; r < ndev; ++r) th.emplace_back(device_phase1, slabs[r], &res[r]);
     for (auto& t : th) t.join();
@@ -1064,13 +1090,27 @@ int gficf_cuda_jaccard_rank(const double* idx, int64_t n, int32_t k, double* out
   s.dev = g_mp.dev;
   s.comm = g_mp.comm;
   SlabResult res;
+  device_phase0(s, &res);
+  DeviceWs& ws = g_ws[s.dev];
+  {
+    // agree that every rank got through its local phase BEFORE the index all-gather: a rank that
+    // failed (out of memory ...) still takes part in this tiny all-reduce, then everybody leaves
+    CU_TRY(cudaSetDevice(s.dev));
+    ws.ensure(s.dev);
+    int* okbit = (int*)((char*)ws.small.p + 48);
+    int h = res.err.code != GFICF_OK;
+    CU_TRY(cudaMemcpyAsync(okbit, &h, sizeof h, cudaMemcpyHostToDevice, ws.s_comp));
+    NCCL_TRY(nccl_dyn::get().AllReduce(okbit, okbit, 1, ncclInt32, ncclMax, s.comm, ws.s_comp));
+    CU_TRY(cudaMemcpyAsync(&h, okbit, sizeof h, cudaMemcpyDeviceToHost, ws.s_comp));
+    CU_TRY(cudaStreamSynchronize(ws.s_comp));
+    if (res.err.code != GFICF_OK) throw res.err;
+    if (h) throw Err{GFICF_E_CUDA, "another rank failed before the index exchange"};
+  }
   device_phase1(s, &res);
   // flags of all ranks (every rank must reach this collective, error or not)
-  DeviceWs& ws = g_ws[s.dev];
   unsigned all_flags = res.flags;
   {
     CU_TRY(cudaSetDevice(s.dev));
-    ws.ensure(s.dev);
     int* bits = (int*)((char*)ws.small.p + 32);
     int h[4] = {(int)(res.flags & 1u), (int)((res.flags >> 1) & 1u), (int)((res.flags >> 2) & 1u),
                 res.err.code != GFICF_OK};

@@ -298,14 +298,30 @@ class PeerGather:
         self.flag_off = (e + 255) // 256 * 256          # [world] chunk flags, then the ack flag
         nbytes = self.flag_off + 4 * (self.world + 1)
         box = [None]
+        ok, self.base = 1, 0
         if self.rank == host_rank:
-            self.base, handle = D.ipc_alloc(nbytes)
-            box = [handle]
+            try:
+                self.base, handle = D.ipc_alloc(nbytes)
+                box = [handle]
+            except Exception:
+                ok = 0
         dist.broadcast_object_list(box, src=host_rank, group=group)
         if self.rank != host_rank:
-            self.base = D.ipc_open(box[0])
+            try:
+                if box[0] is None:
+                    raise RuntimeError("no handle")
+                self.base = D.ipc_open(box[0])
+            except Exception:
+                ok = 0
         self.flags = D.new_flags(torch.device("cuda", torch.cuda.current_device()))
-        dist.barrier(group=group)
+        # every rank learns whether EVERY rank could map the buffer (no peer access between some
+        # GPUs, IPC disabled in a container ...): all raise together, the caller falls back to NCCL
+        agree = torch.tensor([ok], dtype=torch.int32, device=self.flags.device)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=group)
+        if int(agree[0]) == 0:
+            if self.base:
+                (D.ipc_free if self.rank == host_rank else D.ipc_close)(self.base)
+            raise RuntimeError("peer-memory gather unavailable: the count buffer could not be mapped on every rank")
 
     def rows_of(self, rank: int) -> int:
         return sum(p[rank][1] - p[rank][0] for p in self.plan)
