@@ -383,23 +383,27 @@ def run_ours(a):
             # NUMA: every rank runs on the CPUs next to its GPU and first-touches the rows it will
             # move, so the D2H streams of 8 GPUs do not all land on one socket's memory
             numa = multiproc.bind_to_gpu_numa_node(local)
+            numa_aware = numa.startswith("node")  # only then is first-touch placement meaningful
             r_sh = out_sh = None
             if rank == 0:
-                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=True, pin=False)
-                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=True, pin=False)
+                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=True, pin=not numa_aware)
+                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=True, pin=not numa_aware)
+                if not numa_aware:
+                    r_sh.array[...] = synth.to_r_matrix(idx0)
             dist.barrier()
             if rank != 0:
-                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=False, pin=False)
-                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=False, pin=False)
-            s_lo, s_hi = sharding.slab_bounds(n, world, rank)
-            r_sh.first_touch_rows(s_lo, s_hi)
-            out_sh.first_touch_rows(s_lo * k, s_hi * k)
-            dist.barrier()
-            if rank == 0:
-                r_sh.array[...] = synth.to_r_matrix(idx0)
-            dist.barrier()
-            r_sh.pin()
-            out_sh.pin()
+                r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=False, pin=not numa_aware)
+                out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=False, pin=not numa_aware)
+            if numa_aware:
+                s_lo, s_hi = sharding.slab_bounds(n, world, rank)
+                r_sh.first_touch_rows(s_lo, s_hi)
+                out_sh.first_touch_rows(s_lo * k, s_hi * k)
+                dist.barrier()
+                if rank == 0:
+                    r_sh.array[...] = synth.to_r_matrix(idx0)
+                dist.barrier()
+                r_sh.pin()
+                out_sh.pin()
             dist.barrier()
             for _ in range(2):
                 multiproc.rcpp_parallel_jaccard_coef_rank(r_sh.array, out_sh.array)
