@@ -19,6 +19,8 @@ _vp = C.c_void_p
 PROTOTYPES = {
     "gficf_cuda_jaccard": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_int32,
                                      C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]),
+    "gficf_cuda_jaccard_i32": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_int32,
+                                         C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]),
     "gficf_cuda_set_devices": (C.c_int, [C.c_int32]),
     "gficf_cuda_get_devices": (C.c_int, []),
     "gficf_cuda_device_count": (C.c_int, []),

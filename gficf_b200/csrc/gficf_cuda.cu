@@ -230,7 +230,8 @@ int grid_1d(long long total, int block, int cap_per_sm = 8) {
   return (int)g;
 }
 
-void launch_layout(const double* src, long long ld_rows, long long ld_row0, long long n, int k,
+template <typename T>
+void launch_layout(const T* src, long long ld_rows, long long ld_row0, long long n, int k,
                    long long lo, long long hi, int* dst, unsigned* flags, cudaStream_t st) {
   if (hi <= lo) return;
   const int kp = row_stride(k);
@@ -240,8 +241,8 @@ void launch_layout(const double* src, long long ld_rows, long long ld_row0, long
   if (smem > 48 * 1024) throw Err{GFICF_E_LIMIT, "k too large for the layout pre-pass (k <= 12000)"};
   const long long ntiles = (hi - lo + tile_r - 1) / tile_r;
   long long g = std::min<long long>(ntiles, (long long)sm_count() * 8);
-  layout_f64_kernel<<<(int)g, kLayoutThreads, smem, st>>>(src, ld_rows, ld_row0, n, k, kp, lo, hi, dst,
-                                                          flags, tile_r);
+  layout_colmajor_kernel<T><<<(int)g, kLayoutThreads, smem, st>>>(src, ld_rows, ld_row0, n, k, kp, lo, hi,
+                                                                  dst, flags, tile_r);
   CU_TRY(cudaGetLastError());
 }
 
@@ -588,24 +589,21 @@ void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cud
 // Host -> device of a strided 2-D block (rows x cols doubles, source leading dimension ld_src,
 // destination dense with leading dimension rows).  Pinned sources go straight to the copy
 // engine; pageable ones through staged_copy.
-void h2d_block(DeviceWs& ws, const double* src, long long ld_src, double* dst, long long rows,
-               int cols, cudaStream_t st) {
+void h2d_block(DeviceWs& ws, const void* src_v, long long ld_src, void* dst_v, long long rows, int cols,
+               size_t elem, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return;
-  if (is_pinned(src)) {
-    CU_TRY(cudaMemcpy2DAsync(dst, rows * sizeof(double), src, ld_src * sizeof(double),
-                             rows * sizeof(double), cols, cudaMemcpyHostToDevice, st));
-    return;
-  }
-  if ((size_t)rows * cols * sizeof(double) <= kSmallCopyBytes) {
-    // small matrices: the driver's own staging is faster than spinning up the copy threads
-    CU_TRY(cudaMemcpy2DAsync(dst, rows * sizeof(double), src, ld_src * sizeof(double),
-                             rows * sizeof(double), cols, cudaMemcpyHostToDevice, st));
+  const char* src = (const char*)src_v;
+  char* dst = (char*)dst_v;
+  if (is_pinned(src) || (size_t)rows * cols * elem <= kSmallCopyBytes) {
+    // pinned: straight to the copy engine; small: the driver's own staging beats spinning up threads
+    CU_TRY(cudaMemcpy2DAsync(dst, rows * elem, src, ld_src * elem, rows * elem, cols, cudaMemcpyHostToDevice,
+                             st));
     return;
   }
   std::vector<Seg> segs;
   for (int c = 0; c < cols; ++c)
-    segs.push_back({(char*)(src + (long long)c * ld_src), (char*)(dst + (long long)c * rows),
-                    (size_t)rows * sizeof(double), nullptr});
+    segs.push_back({(char*)(src + (size_t)c * ld_src * elem), dst + (size_t)c * rows * elem,
+                    (size_t)rows * elem, nullptr});
   staged_copy(ws, segs, true, st);
 }
 
@@ -639,9 +637,10 @@ struct Slab {
   int dev;                    // CUDA device ordinal (== rank inside one process)
   ncclComm_t comm = nullptr;  // communicator of this rank when ndev > 1
   long long n, rows_per, lo, hi, rows, E, slab_e;
-  const double* h_idx;
+  const void* h_idx;
+  int elem = 8;  // bytes per element of the caller's matrix: 8 = double, 4 = int32
   double* h_out;
-  Slab(int rank_, int ndev_, const double* h_idx_, long long n_, int k_, long long rows_per_,
+  Slab(int rank_, int ndev_, const void* h_idx_, long long n_, int k_, long long rows_per_,
        double* h_out_, int mode_)
       : rank(rank_), ndev(ndev_), k(k_), kp(row_stride(k_)), mode(mode_), dev(rank_), n(n_),
         rows_per(rows_per_), h_idx(h_idx_), h_out(h_out_) {
@@ -692,7 +691,7 @@ void device_phase0(Slab s, SlabResult* res) {
     ws.ensure(s.dev);
     const int k = s.k;
     const int cbytes = k <= 255 ? 1 : 2;
-    ws.in_f64.need(std::max<size_t>(16, (size_t)s.rows * k * sizeof(double)));
+    ws.in_f64.need(std::max<size_t>(16, (size_t)s.rows * k * s.elem));
     ws.idx.need(std::max<size_t>(16, (size_t)s.rows_per * s.ndev * s.kp * sizeof(int)));
     ws.out.need(std::max<size_t>(16, (size_t)s.slab_e * 3 * sizeof(double)));
     if (s.mode == GFICF_MODE_SERIAL || k > kLargeMaxK) {
@@ -702,10 +701,15 @@ void device_phase0(Slab s, SlabResult* res) {
     unsigned* d_flags = (unsigned*)ws.small.p;
     CU_TRY(cudaMemsetAsync(ws.small.p, 0, 64, ws.s_comp));
     CU_TRY(cudaEventRecord(ws.ev[0], ws.s_comp));
-    h2d_block(ws, s.h_idx + s.lo, s.n, (double*)ws.in_f64.p, s.rows, k, ws.s_comp);
+    h2d_block(ws, (const char*)s.h_idx + (size_t)s.lo * s.elem, s.n, ws.in_f64.p, s.rows, k, s.elem,
+              ws.s_comp);
     CU_TRY(cudaEventRecord(ws.ev[1], ws.s_comp));
-    launch_layout((const double*)ws.in_f64.p, s.rows, s.lo, s.n, k, s.lo, s.hi, (int*)ws.idx.p, d_flags,
-                  ws.s_comp);
+    if (s.elem == 8)
+      launch_layout((const double*)ws.in_f64.p, s.rows, s.lo, s.n, k, s.lo, s.hi, (int*)ws.idx.p, d_flags,
+                    ws.s_comp);
+    else
+      launch_layout((const int*)ws.in_f64.p, s.rows, s.lo, s.n, k, s.lo, s.hi, (int*)ws.idx.p, d_flags,
+                    ws.s_comp);
     res->launches += s.rows > 0;
     CU_TRY(cudaEventRecord(ws.ev[2], ws.s_comp));
   } catch (const Err& e) {
@@ -938,8 +942,11 @@ int gficf_cuda_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, i
   return GFICF_OK;
 }
 
-int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int32_t n_devices,
-                       int32_t mode, int64_t* n_written, char* err, size_t errlen) {
+}  // extern "C"
+
+namespace {
+int jaccard_host_call(const void* idx, int elem, int64_t n, int32_t k, double* out, int32_t n_devices,
+                      int32_t mode, int64_t* n_written, char* err, size_t errlen) {
   API_BEGIN
   if (err && errlen) err[0] = 0;
   if (n < 0 || k < 0) throw Err{GFICF_E_ARG, "negative matrix dimension"};
@@ -969,7 +976,10 @@ int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int
   g_active_devices.store(ndev);
   std::vector<SlabResult> res(ndev);
   std::vector<Slab> slabs;
-  for (int r = 0; r < ndev; ++r) slabs.emplace_back(r, ndev, idx, (long long)n, (int)k, rows_per, out, (int)mode);
+  for (int r = 0; r < ndev; ++r) {
+    slabs.emplace_back(r, ndev, idx, (long long)n, (int)k, rows_per, out, (int)mode);
+    slabs.back().elem = elem;
+  }
   auto first_error = [&]() {
     for (auto& r : res)
       if (r.err.code != GFICF_OK) throw r.err;
@@ -1029,6 +1039,19 @@ int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int
   if (n_written) *n_written = res[0].n_written;
   return GFICF_OK;
   API_END
+}
+}  // namespace
+
+extern "C" {
+
+int gficf_cuda_jaccard(const double* idx, int64_t n, int32_t k, double* out, int32_t n_devices,
+                       int32_t mode, int64_t* n_written, char* err, size_t errlen) {
+  return jaccard_host_call(idx, 8, n, k, out, n_devices, mode, n_written, err, errlen);
+}
+
+int gficf_cuda_jaccard_i32(const int32_t* idx, int64_t n, int32_t k, double* out, int32_t n_devices,
+                           int32_t mode, int64_t* n_written, char* err, size_t errlen) {
+  return jaccard_host_call(idx, 4, n, k, out, n_devices, mode, n_written, err, errlen);
 }
 
 // ---------------------------------------------------------------- one process per GPU

@@ -1,7 +1,7 @@
 // jaccard_kernels.cuh -- sm_100a device kernels of the Phenograph Jaccard path.
 //
 // What they replace (reference = dibbelab/gficf):
-//   layout_f64_kernel      the per-edge strided row copies out of the column-major
+//   layout_colmajor_kernel the per-edge strided row copies out of the column-major
 //                          double matrix, src/rcpp_parallel_jaccard_coeff.cpp:30-36
 //   jaccard_small_k_kernel JCoefficient::operator() for k<=32,
 //   jaccard_wide_k_kernel  and for 32<k<=128, rcpp_parallel_jaccard_coeff.cpp:24-55
@@ -130,8 +130,31 @@ __device__ __forceinline__ double jaccard_weight(int u, int k) {
 constexpr int kLayoutTileR = 64;  // rows per tile (halved by the host until the tile fits 48 KB)
 constexpr int kLayoutThreads = 256;
 
+// id of one element of the caller's matrix: T = double (R numeric matrix) or int (R integer
+// matrix, NA_integer_ = INT_MIN is out of range like any other bad id); returns false for a bad id
+template <typename T>
+__device__ __forceinline__ bool id_from_r(T d, long long n, int& v);
+template <>
+__device__ __forceinline__ bool id_from_r<double>(double d, long long n, int& v) {
+  // ids must be integers in [1,n]; NaN fails the first comparison
+  if (d >= 1.0 && d <= (double)n && d == floor(d)) {
+    v = (int)d - 1;  // :28  int k = mat(i,j)-1
+    return true;
+  }
+  return false;
+}
+template <>
+__device__ __forceinline__ bool id_from_r<int>(int d, long long n, int& v) {
+  if (d >= 1 && (long long)d <= n) {
+    v = d - 1;
+    return true;
+  }
+  return false;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kLayoutThreads)
-layout_f64_kernel(const double* __restrict__ src, long long ld_rows, long long ld_row0, long long n,
+layout_colmajor_kernel(const T* __restrict__ src, long long ld_rows, long long ld_row0, long long n,
                   int k, int kp, long long row_lo, long long row_hi, int* __restrict__ dst,
                   unsigned* __restrict__ flags, int tile_r) {
   extern __shared__ int tile[];  // [tile_r][kp + 1]
@@ -147,11 +170,8 @@ layout_f64_kernel(const double* __restrict__ src, long long ld_rows, long long l
     for (int j = tid / tile_r; j < kp; j += kLayoutThreads / tile_r) {
       int v = kPadId;
       if (j < k && r < rows) {
-        const double d = __ldcs(src + (long long)j * ld_rows + (r0 + r - ld_row0));
-        // ids must be integers in [1,n]; NaN fails the first comparison
-        if (d >= 1.0 && d <= (double)n && d == floor(d)) {
-          v = (int)d - 1;  // :28  int k = mat(i,j)-1
-        } else {
+        const T d = __ldcs(src + (long long)j * ld_rows + (r0 + r - ld_row0));
+        if (!id_from_r<T>(d, n, v)) {
           bad = true;
           v = 0;
         }

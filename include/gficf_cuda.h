@@ -80,6 +80,14 @@ int gficf_cuda_jaccard(const double* idx_colmajor, int64_t n, int32_t k, double*
                        int32_t n_devices, int32_t mode, int64_t* n_written, char* err,
                        size_t errlen);
 
+/* Same call on an INTEGER matrix (R INTSXP: int32, column-major, 1-based; NA_integer_ is rejected
+ * like any out-of-range id).  uwot hands clustcells() an integer matrix, which the reference's
+ * shim coerces to double first (src/RcppExports.cpp:65); taking it as it is halves the H2D bytes
+ * (SURVEY 8f row 2). */
+int gficf_cuda_jaccard_i32(const int32_t* idx_colmajor, int64_t n, int32_t k, double* out_colmajor,
+                           int32_t n_devices, int32_t mode, int64_t* n_written, char* err,
+                           size_t errlen);
+
 /* Device-count option that R/clustCells.R's new `n.gpu` argument sets without
  * changing the arity of the registered .Call routines
  * (src/RcppExports.cpp:85-92).  Also read once from the environment variable

@@ -101,11 +101,22 @@ def test_self_in_own_list_and_identical_lists(cuda, oracle):
     assert (out[0::30, 2] == 1.0).all()
 
 
-def test_integer_matrix_is_coerced_like_rcpp(cuda, oracle):
+def test_integer_matrix_takes_the_int32_entry(cuda, oracle):
+    """uwot returns an INTEGER matrix; it is consumed as int32 (gficf_cuda_jaccard_i32), other
+    integer widths are coerced to double like Rcpp does."""
     rng = np.random.default_rng(2)
-    idx = random_knn(rng, 300, 15)
-    as_int = np.ascontiguousarray(idx.astype(np.int32))  # C order, integer: what uwot returns
-    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(as_int), oracle.parallel(idx))
+    for n, k in ((300, 15), (50_000, 30), (2_000, 100)):
+        idx = random_knn(rng, n, k)
+        want = oracle.parallel(idx)
+        as_int = np.ascontiguousarray(idx.astype(np.int32))  # C order, int32
+        assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(as_int), want)
+        assert np.array_equal(cuda.jaccard_coeff(np.asfortranarray(as_int)), oracle.serial(idx))
+        assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(idx.astype(np.int64)), want)
+    bad = random_knn(rng, 100, 5).astype(np.int32)
+    bad[7, 2] = np.iinfo(np.int32).min  # NA_integer_
+    with pytest.raises(cuda.GficfCudaError) as e:
+        cuda.rcpp_parallel_jaccard_coef(bad)
+    assert e.value.code == 2
 
 
 def test_invalid_ids_are_rejected(cuda):
