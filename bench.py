@@ -91,6 +91,15 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
+    def sample_once(self):
+        """One synchronous sample (NVML calls can take tens of ms: the thread alone may see few)."""
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+
     def _loop(self):
         nv = self.nv
         names = {
@@ -117,6 +126,7 @@ class ClockSampler:
             self._t.start()
 
     def stop(self):
+        self.sample_once()  # right behind the last timed kernel
         if self._t is not None:
             self._stop.set()
             self._t.join()
