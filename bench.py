@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunks", type=int, default=4, help="N>1: row chunks of the pipelined gather")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N>1: how the counts reach the host rank (fused peer stores / NCCL send-recv)")
     return ap.parse_args()
@@ -265,7 +266,7 @@ def run_ours(a):
         counts_all = torch.empty(E, dtype=torch.uint8, device=dev)
         if a.gather == "peer":
             try:
-                pg = sharding.PeerGather(n, k, rho=rho, chunks=4)
+                pg = sharding.PeerGather(n, k, rho=rho, chunks=a.chunks)
             except RuntimeError as ex:  # raised on every rank together
                 sys.stderr.write("bench.py: %s; falling back to NCCL send/recv\n" % ex)
                 a.gather = "nccl"
@@ -274,7 +275,7 @@ def run_ours(a):
             def step():
                 pg.step(padded, out)
         else:
-            pg = sharding.PipelinedGather(n, k, rho=rho, chunks=4)
+            pg = sharding.PipelinedGather(n, k, rho=rho, chunks=a.chunks)
 
             def step():
                 pg.step(padded, counts_all, out)
@@ -511,9 +512,9 @@ def run_ours(a):
                              % (n * 32 * 4 / 1e6),
                        "sharding": "none" if world == 1 else
                        "rows over %d ranks, host rank takes %.1f%% (expand/count cost ratio %.3f measured); resident "
-                       "replicated int32 index; 4 chunks per rank; u8 counts reach rank 0 %s; expand kernel on rank 0 "
+                       "replicated int32 index; %d chunks per rank; u8 counts reach rank 0 %s; expand kernel on rank 0 "
                        "overlapping the next chunk" % (
-                           world, 100.0 * host_share, rho,
+                           world, 100.0 * host_share, rho, a.chunks,
                            "by peer stores from the count kernel's epilogue (CUDA IPC mapping over NVLink, flag per "
                            "chunk)" if a.gather == "peer" else "over NCCL send/recv as counted"),
                        "launch": {"grid": g.value, "block": b.value, "smem": s.value}},

@@ -41,7 +41,7 @@ PROTOTYPES = {
     "gficf_cuda_signal_dev": (C.c_int, [_vp, C.c_uint32, _vp]),
     "gficf_cuda_wait_dev": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "gficf_cuda_expand_wait_dev": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp,
-                                             C.c_int32, C.c_uint32, _vp, _vp]),
+                                             C.c_int32, C.c_uint32, C.c_int64, _vp, _vp]),
     "gficf_cuda_row_stride": (C.c_int32, [C.c_int32]),
     "gficf_cuda_layout_dev": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
                                         C.c_int64, _vp, _vp, _vp]),

@@ -273,7 +273,7 @@ void launch_expand_t(const int* idx, int k, long long lo, long long hi, const CT
   if (total <= 0) return;
   if (mode == GFICF_MODE_PARALLEL) {
     expand_fixed_kernel<CT><<<grid_1d(total, kExpandThreads, 8), kExpandThreads, 0, st>>>(
-        idx, k, kp, lo, hi, d_u, f, t, w, nullptr, 0, 0u, nullptr);
+        idx, k, kp, lo, hi, d_u, f, t, w, nullptr, 0, 0u, 0, nullptr);
   } else {
     long long* chunk = (long long*)scratch;
     const long long nchunks = (total + kCompactChunk - 1) / kCompactChunk;
@@ -1236,7 +1236,7 @@ int gficf_cuda_wait_dev(const uint32_t* d_flag, uint32_t expected, uint32_t* d_f
 int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, int64_t row_hi,
                                const uint8_t* d_u, double* d_from, double* d_to, double* d_w,
                                const uint32_t* d_ready, int32_t n_ready, uint32_t expected,
-                               uint32_t* d_flags, void* stream) {
+                               int64_t chunk_rows, uint32_t* d_flags, void* stream) {
   char* err = nullptr;
   size_t errlen = 0;
   API_BEGIN
@@ -1245,7 +1245,8 @@ int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_
   const long long total = (row_hi - row_lo) * (long long)k;
   if (total <= 0) return GFICF_OK;
   expand_fixed_kernel<uint8_t><<<grid_1d(total, kExpandThreads, 8), kExpandThreads, 0, (cudaStream_t)stream>>>(
-      d_idx_i32, k, row_stride(k), row_lo, row_hi, d_u, d_from, d_to, d_w, d_ready, n_ready, expected, d_flags);
+      d_idx_i32, k, row_stride(k), row_lo, row_hi, d_u, d_from, d_to, d_w, d_ready, n_ready, expected,
+      chunk_rows, d_flags);
   CU_TRY(cudaGetLastError());
   return GFICF_OK;
   API_END

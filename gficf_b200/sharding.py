@@ -292,6 +292,7 @@ class PeerGather:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.plan = chunk_major_bounds(n, self.world, rho, chunks, host_rank)
         self.nchunks = len(self.plan)
+        self.chunk_rows = self.plan[0][-1][1] - self.plan[0][0][0]  # rows per chunk (the last may be shorter)
         self.epoch = 0
         self.launches = 0
         e = n * k
@@ -344,6 +345,11 @@ class PeerGather:
         if self.rank != self.host:
             # the host rank must have consumed the previous step's counts before they are overwritten
             D.wait_flag(ack, self.epoch, self.flags)
+        # every rank: its part of chunk c, then a flag raise in the host rank's memory; the host rank
+        # follows each of its own parts with the expand launch of that chunk (which waits for every
+        # rank's flag), so expanding chunk c overlaps everybody's counting of chunk c+1.
+        # (One single expand launch streaming behind the chunks -- expand_wait(chunk_rows=...) -- was
+        # measured slower: 1.46 vs 1.19 ms at 4 ranks, 2.30 vs 2.04 ms at 2.)
         for c, ranges in enumerate(self.plan):
             lo, hi = ranges[self.rank]
             if hi > lo:

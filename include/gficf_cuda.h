@@ -145,7 +145,9 @@ int gficf_cuda_jaccard_rank(const double* idx_colmajor, int64_t n, int32_t k, do
  *  rank's HBM.  gficf_cuda_signal_dev raises a flag in that buffer when the
  *  stream reaches it; gficf_cuda_expand_wait_dev is the expand kernel that first
  *  waits until d_ready[0..n_ready) >= expected, one flag per contributing rank
- *  (bounded spin; GFICF_FLAG_PEER_TIMEOUT on give-up).
+ *  (bounded spin; GFICF_FLAG_PEER_TIMEOUT on give-up).  With chunk_rows > 0 the rows
+ *  are expanded chunk by chunk in ONE launch: chunk c waits for the flags to reach
+ *  expected + c, so the kernel streams behind ranks that are still counting.
  * ======================================================================== */
 #define GFICF_IPC_HANDLE_BYTES 64
 #define GFICF_FLAG_PEER_TIMEOUT 8u
@@ -158,7 +160,7 @@ int gficf_cuda_wait_dev(const uint32_t* d_flag, uint32_t expected, uint32_t* d_f
 int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, int64_t row_hi,
                                const uint8_t* d_u, double* d_from, double* d_to, double* d_w,
                                const uint32_t* d_ready, int32_t n_ready, uint32_t expected,
-                               uint32_t* d_flags, void* stream);
+                               int64_t chunk_rows, uint32_t* d_flags, void* stream);
 
 /* ======================================================================== *
  *  Device-buffer entry points (resident data: the benchmarked kernels, and
