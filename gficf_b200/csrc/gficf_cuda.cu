@@ -344,7 +344,8 @@ struct DeviceWs {
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_chunk[kMaxChunks] = {};
   cudaEvent_t ev_k0[kMaxChunks] = {}, ev_k1[kMaxChunks] = {};
-  Buf in_f64, idx, out, counts, scratch, small;  // small: flags (4B) + n_written (8B)
+  // in_raw: device copy of the caller's rows (f64 or int32, column-major); small: flags + n_written
+  Buf in_raw, idx, out, counts, scratch, small;
   PinBuf ring;
   cudaEvent_t ev_slot[kStageSlots] = {};
   unsigned* h_small = nullptr;  // pinned mirror of `small`
@@ -368,7 +369,7 @@ struct DeviceWs {
     if (!init) return;
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
-    in_f64.drop(); idx.drop(); out.drop(); counts.drop(); scratch.drop(); small.drop();
+    in_raw.drop(); idx.drop(); out.drop(); counts.drop(); scratch.drop(); small.drop();
     ring.drop();
     if (h_small) cudaFreeHost(h_small);
     h_small = nullptr;
@@ -691,7 +692,7 @@ void device_phase0(Slab s, SlabResult* res) {
     ws.ensure(s.dev);
     const int k = s.k;
     const int cbytes = k <= 255 ? 1 : 2;
-    ws.in_f64.need(std::max<size_t>(16, (size_t)s.rows * k * s.elem));
+    ws.in_raw.need(std::max<size_t>(16, (size_t)s.rows * k * s.elem));
     ws.idx.need(std::max<size_t>(16, (size_t)s.rows_per * s.ndev * s.kp * sizeof(int)));
     ws.out.need(std::max<size_t>(16, (size_t)s.slab_e * 3 * sizeof(double)));
     if (s.mode == GFICF_MODE_SERIAL || k > kLargeMaxK) {
@@ -701,14 +702,14 @@ void device_phase0(Slab s, SlabResult* res) {
     unsigned* d_flags = (unsigned*)ws.small.p;
     CU_TRY(cudaMemsetAsync(ws.small.p, 0, 64, ws.s_comp));
     CU_TRY(cudaEventRecord(ws.ev[0], ws.s_comp));
-    h2d_block(ws, (const char*)s.h_idx + (size_t)s.lo * s.elem, s.n, ws.in_f64.p, s.rows, k, s.elem,
+    h2d_block(ws, (const char*)s.h_idx + (size_t)s.lo * s.elem, s.n, ws.in_raw.p, s.rows, k, s.elem,
               ws.s_comp);
     CU_TRY(cudaEventRecord(ws.ev[1], ws.s_comp));
     if (s.elem == 8)
-      launch_layout((const double*)ws.in_f64.p, s.rows, s.lo, s.n, k, s.lo, s.hi, (int*)ws.idx.p, d_flags,
+      launch_layout((const double*)ws.in_raw.p, s.rows, s.lo, s.n, k, s.lo, s.hi, (int*)ws.idx.p, d_flags,
                     ws.s_comp);
     else
-      launch_layout((const int*)ws.in_f64.p, s.rows, s.lo, s.n, k, s.lo, s.hi, (int*)ws.idx.p, d_flags,
+      launch_layout((const int*)ws.in_raw.p, s.rows, s.lo, s.n, k, s.lo, s.hi, (int*)ws.idx.p, d_flags,
                     ws.s_comp);
     res->launches += s.rows > 0;
     CU_TRY(cudaEventRecord(ws.ev[2], ws.s_comp));
