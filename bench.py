@@ -52,10 +52,21 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--chunks", type=int, default=4, help="N>1: row chunks of the pipelined gather")
+    ap.add_argument("--chunks", type=int, default=4, help="N>1, --gather nccl: row chunks of the pipelined gather")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N>1: how the counts reach the host rank (fused peer stores / NCCL send-recv)")
-    return ap.parse_args()
+                    help="N>1: how the counts reach the host rank (streaming peer stores / NCCL send-recv)")
+    ap.add_argument("--config", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs[i-1]; cfg4 (4M x 30) is the one the metric is quoted on")
+    ap.add_argument("--host-share", type=float, default=-1.0, help="N>1: host rank's row share (default: calibrated)")
+    ap.add_argument("--no-traffic-probe", action="store_true", help="do not re-run the kernel under ncu for roofline.traffic")
+    ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-parity", action="store_true")
+    a = ap.parse_args()
+    shapes = {"cfg1": (10_000, 15), "cfg2": (100_000, 30), "cfg3": (1_000_000, 30), "cfg4": (4_000_000, 30),
+              "cfg5": (10_000_000, 100)}
+    if a.config != "cfg4":
+        a.cells, a.k = shapes[a.config]
+    return a
 
 
 def workload_name(a):
@@ -198,6 +209,94 @@ def run_reference_arm(a):
     }))
 
 
+def checker():
+    """The CPU checker for parity records: oracle/_ref (the reference's own sources) when it was
+    built in the container, else the C restatement."""
+    from oracle.binding import Oracle, Reference
+
+    if Reference.available():
+        return Reference(), "reference"
+    return Oracle(), "port"
+
+
+def parity_ranges(n, rows=2000):
+    """Head, middle and tail row ranges (>= 2000 rows each when the matrix has them)."""
+    rows = min(rows, n)
+    mid = max(0, min(n - rows, n // 2 - rows // 2))
+    out = []
+    for lo in (0, mid, n - rows):
+        if (lo, lo + rows) not in out:
+            out.append((lo, lo + rows))
+    return out
+
+
+def rows_equal(chk, r_matrix, k, ranges, getter):
+    """getter(lo, hi) -> ((hi-lo)*k, 3) numpy block of a result; compared with the checker bit for bit."""
+    import numpy as np
+
+    ok = True
+    for lo, hi in ranges:
+        want = chk.parallel_rows(r_matrix, lo, hi)
+        ok = ok and bool(np.array_equal(getter(lo, hi), want))
+    return ok
+
+
+def probe_traffic(a):
+    """roofline.traffic measured in THIS run: the fused kernel of this workload once more under
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` in a child process (never the timed
+    process).  Returns (bytes per launch, source) or (None, why)."""
+    import shutil
+    import subprocess
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+           "--profile-from-start", "off", "-k", "regex:jaccard_(small|wide|large)_k", "-c", "1", "--csv",
+           sys.executable, os.path.abspath(__file__), "--traffic-probe", "--cells", str(a.cells), "--k", str(a.k),
+           "--family", a.family, "--seed", str(a.seed)] + (["--no-scramble"] if a.no_scramble else [])
+    try:
+        env = dict(os.environ)
+        for v in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+            env.pop(v, None)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+        tot = 0.0
+        seen = 0
+        for ln in r.stdout.splitlines():
+            if "dram__bytes_" in ln:
+                f = [x.strip('"') for x in ln.split('","')]
+                unit, val = f[-2], float(f[-1].replace(",", ""))
+                tot += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1.0)
+                seen += 1
+        if seen >= 2:
+            return tot, "ncu dram__bytes_read.sum+dram__bytes_write.sum, one launch, captured in this run"
+        return None, "ncu gave no counters (rc %d): %s" % (r.returncode, (r.stdout + r.stderr)[-200:].replace("\n", " "))
+    except Exception as ex:
+        return None, "ncu probe failed: %s" % str(ex)[:120]
+
+
+def run_traffic_probe(a):
+    """Child of probe_traffic(): builds the workload and launches the fused kernel three times."""
+    import torch
+
+    from gficf_b200 import device as D
+    from gficf_b200 import synth
+
+    dev = torch.device("cuda", 0)
+    idx0 = synth.knn_index(a.cells, a.k, family=a.family, seed=a.seed, scramble=not a.no_scramble, device=dev)
+    padded, flags = D.pad_rows(idx0)
+    del idx0
+    out = torch.empty((3, a.cells * a.k), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    for i in range(3):
+        flush.fill_(i)
+        D.jaccard_edges(padded, a.cells, a.k, out=out, flags=flags)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_ours(a):
     import numpy as np
@@ -217,7 +316,6 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the chunk sends must get SMs while the persistent count kernels own the GPU
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
     gficf_b200.lib()  # fail loudly now if the extension is missing
@@ -226,6 +324,7 @@ def run_ours(a):
     E = n * k
     bytes_per_edge = 4 * k + 28
     hbm_peak, peak_src = peaks()
+    warm = max(3, a.warmup)
 
     # ---- inputs: every rank generates the same matrix (counter-based generator)
     idx0 = synth.knn_index(n, k, family=a.family, seed=a.seed, scramble=not a.no_scramble, device=dev)
@@ -234,60 +333,77 @@ def run_ours(a):
     assert int(flags[0]) == 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    lo, hi = sharding.slab_bounds(n, world, rank)
+    def event_ms(fn, reps=5, warmups=2):
+        for _ in range(warmups):
+            fn()
+        ts = []
+        for i in range(reps):
+            flush.fill_(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    sharding_note = "none"
+    pg = None
     if world == 1:
         out = torch.empty((3, E), dtype=torch.float64, device=dev)
+        lo, hi = 0, n
 
         def step():
             D.jaccard_edges(padded, n, k, out=out, flags=flags)
-        launches_per_step = 1
     else:
-        # calibrate the uneven row split: rho = expand time per row / count time per row (this GPU)
+        out = torch.empty((3, E), dtype=torch.float64, device=dev) if rank == 0 else None
+        # calibrate the uneven row split on this GPU: per-row cost of the fused kernel (host rank's own
+        # rows), the count kernel (peers' rows) and the expand kernel (host rank, every peer row)
         m = min(n, 1_000_000)
         cal_c = torch.empty(m * k, dtype=torch.uint8, device=dev)
         cal_o = torch.empty((3, m * k), dtype=torch.float64, device=dev)
-        t = []
-        for fn in (lambda: D.jaccard_counts(padded, n, k, 0, m, out=cal_c, flags=flags),
-                   lambda: D.expand(padded, k, cal_c, mode=0, row_lo=0, row_hi=m, out=cal_o)):
-            for _ in range(2):
-                fn()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            t.append(e0.elapsed_time(e1) / 5)
+        t_fused = event_ms(lambda: D.jaccard_edges(padded, n, k, 0, m, out=cal_o, flags=flags))
+        t_count = event_ms(lambda: D.jaccard_counts(padded, n, k, 0, m, out=cal_c, flags=flags))
+        t_expand = event_ms(lambda: D.expand(padded, k, cal_c, mode=0, row_lo=0, row_hi=m, out=cal_o))
         del cal_c, cal_o
-        rho_t = torch.tensor([t[1] / t[0]], dtype=torch.float64, device=dev)
-        dist.broadcast(rho_t, src=0)  # every rank must use the same split
-        rho = float(rho_t[0])
-        out = torch.empty((3, E), dtype=torch.float64, device=dev) if rank == 0 else None
-        counts_all = torch.empty(E, dtype=torch.uint8, device=dev)
-        if a.gather == "peer":
+        cal = torch.tensor([t_fused, t_count, t_expand], dtype=torch.float64, device=dev)
+        dist.broadcast(cal, src=0)  # every rank must use the same split
+        t_fused, t_count, t_expand = (float(x) for x in cal)
+        share = a.host_share if a.host_share >= 0 else sharding.balanced_host_share(world, t_fused, t_count, t_expand)
+        if a.gather == "peer" and k <= 127:
             try:
-                pg = sharding.PeerGather(n, k, rho=rho, chunks=a.chunks)
+                pg = sharding.PeerGather(n, k, host_share=share)
             except RuntimeError as ex:  # raised on every rank together
                 sys.stderr.write("bench.py: %s; falling back to NCCL send/recv\n" % ex)
                 a.gather = "nccl"
+        else:
+            a.gather = "nccl"
         if a.gather == "peer":
+            pg.flags = flags
 
             def step():
                 pg.step(padded, out)
+            lo, hi = pg.bounds[rank]
+            host_share = pg.rows_of(0) / n
+            sharding_note = (
+                "rows over %d ranks, host rank takes %.1f%% (calibrated on this GPU: fused %.3f / count %.3f / expand "
+                "%.3f ms per 1M rows); resident replicated int32 index; ONE persistent count launch per rank whose "
+                "epilogue stores the parity-tagged u8 counts into rank 0's HBM (CUDA IPC mapping over NVLink); rank 0: "
+                "fused kernel on its own rows, then ONE streaming expand launch that polls the count bytes (no flags, "
+                "no per-chunk launches)" % (world, 100.0 * host_share, t_fused * 1e6 / m, t_count * 1e6 / m,
+                                           t_expand * 1e6 / m))
         else:
-            pg = sharding.PipelinedGather(n, k, rho=rho, chunks=a.chunks)
+            counts_all = torch.empty(E, dtype=torch.uint8 if k <= 255 else torch.int16, device=dev)
+            pg = sharding.PipelinedGather(n, k, rho=t_expand / t_count, chunks=a.chunks)
+            pg.flags = flags
 
             def step():
                 pg.step(padded, counts_all, out)
-        pg.flags = flags
-        if a.gather == "peer":  # a contiguous range of this rank's row count, for the kernel-only timing
-            lo = min(pg.plan[0][rank][0], n - pg.rows_of(rank))
-            hi = lo + pg.rows_of(rank)
-            host_share = pg.rows_of(0) / n
-        else:
             lo, hi = pg.bounds[rank]
             host_share = (pg.bounds[0][1] - pg.bounds[0][0]) / n
-        launches_per_step = None  # counted by pg
+            sharding_note = ("rows over %d ranks, host rank takes %.1f%%; resident replicated int32 index; %d chunks per "
+                             "rank; u8 counts reach rank 0 over NCCL send/recv as counted; expand kernel on rank 0 "
+                             "overlapping the next chunk" % (world, 100.0 * host_share, a.chunks))
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,14 +412,13 @@ def run_ours(a):
             torch.cuda.synchronize()
 
     torch.cuda.profiler.start()  # ncu --profile-from-start off: skip the input generator's launches
-    for _ in range(max(3, a.warmup)):
+    for _ in range(warm):
         step()
     barrier()
+    launches0 = pg.launches if pg is not None else 0
     sampler = ClockSampler(local)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    kev0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    kev1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     sampler.start()
     t_wall0 = time.perf_counter()
     for i in range(a.steps):
@@ -317,82 +432,117 @@ def run_ours(a):
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     step_ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in zip(ev0, ev1)], dtype=torch.float64, device=dev)
+    gather_flags = 0
     if world > 1:
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # max over ranks, per step
-        # the dominant kernel alone (count kernel over this rank's slab), for the roofline record
-        nl = pg.launches
-        kt = []
-        if hi > lo:
-            for _ in range(3):
-                D.jaccard_counts(padded, n, k, lo, hi, out=counts_all[lo * k:hi * k], flags=flags)
-            for i in range(5):
-                flush.fill_(i)
-                kev0[0].record()
-                D.jaccard_counts(padded, n, k, lo, hi, out=counts_all[lo * k:hi * k], flags=flags)
-                kev1[0].record()
-                torch.cuda.synchronize()
-                kt.append(kev0[0].elapsed_time(kev1[0]))
-        kern_t = torch.tensor([sum(kt) / len(kt) if kt else 0.0, float(hi - lo), float(nl)], dtype=torch.float64, device=dev)
+        nl = pg.launches - launches0
+        if a.gather == "peer":
+            gather_flags = pg.finish(padded, out)  # collective: raises on a peer timeout, exact path on repeated ids
+        # the dominant kernel alone (count kernel over this rank's rows; rank 0: its fused kernel), for the roofline
+        scratch = torch.empty(max(1, (hi - lo) * k), dtype=torch.uint8 if k <= 255 else torch.int16, device=dev)
+        kt = event_ms(lambda: D.jaccard_counts(padded, n, k, lo, hi, out=scratch, flags=flags), reps=5, warmups=3) \
+            if hi > lo else 0.0
+        del scratch
+        kern_t = torch.tensor([kt, float(hi - lo), float(nl)], dtype=torch.float64, device=dev)
         allk = [torch.zeros_like(kern_t) for _ in range(world)]
         dist.all_gather(allk, kern_t)
         slowest = max(allk, key=lambda v: float(v[0]))
-        kern_ms = slowest[:1]
+        kern_avg_ms = float(slowest[0])
         kern_rows = int(slowest[1])
         total_launches = int(sum(float(v[2]) for v in allk))
     else:
-        kern_ms = step_ms
-    assert int(flags[0]) == 0, "fast kernel flagged the synthetic input"
+        kern_avg_ms = float(step_ms.mean())
+    assert int(flags[0]) == 0 and gather_flags == 0, "fast kernel flagged the synthetic input"
     total_ms = float(step_ms.sum())
     ms_per_step = total_ms / a.steps
     value = E / (ms_per_step * 1e-3)
-    kern_avg_ms = float(kern_ms.mean())
     edges_per_launch = E if world == 1 else kern_rows * k
     bpe = bytes_per_edge if world == 1 else (4 * k + 4 + 1)  # count kernel writes 1 B/edge
     achieved = edges_per_launch * bpe / (kern_avg_ms * 1e-3) / 1e9
 
-    # ---- end to end through the reference-facing call, host buffers (pinned)
+    # ---- parity of the value path (rank 0): the checker on head / middle / tail rows, and at N>1 the
+    #      whole matrix against the single-GPU fused kernel
+    parity = None
+    r_host_matrix = None
+    if rank == 0 and not a.no_parity:
+        chk, chk_kind = checker()
+        r_host_matrix = synth.to_r_matrix(idx0)
+        ranges = parity_ranges(n)
+        parity = {"checker": chk_kind, "oracle_rows": ranges,
+                  "value_path_equals_oracle": rows_equal(
+                      chk, r_host_matrix, k, ranges, lambda lo_, hi_: out[:, lo_ * k:hi_ * k].cpu().numpy().T)}
+        if world > 1:
+            single = torch.empty((3, E), dtype=torch.float64, device=dev)
+            fl1 = D.new_flags(dev)
+            D.jaccard_edges(padded, n, k, out=single, flags=fl1)
+            torch.cuda.synchronize()
+            parity["full_matrix_equal"] = bool(torch.equal(single, out)) and int(fl1[0]) == 0
+            parity["full_matrix_vs"] = "single-GPU fused kernel on rank 0, torch.equal over all 3 x %d doubles" % E
+            del single
+
+    # ---- end to end through the reference-facing call, host buffers
     e2e = None
     if not a.no_e2e:
         e2e_steps = a.e2e_steps or min(a.steps, 10)
         if world == 1:
+            if r_host_matrix is None:
+                r_host_matrix = synth.to_r_matrix(idx0)
+
+            def timed_call(mat, outbuf, reps, env=None):
+                old = {}
+                for kk, vv in (env or {}).items():
+                    old[kk] = os.environ.get(kk)
+                    os.environ[kk] = vv
+                try:
+                    gficf_b200.rcpp_parallel_jaccard_coef(mat, False, 1, out=outbuf)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(reps):
+                        gficf_b200.rcpp_parallel_jaccard_coef(mat, False, 1, out=outbuf)
+                    dt = (time.perf_counter() - t0) / reps
+                finally:
+                    for kk, vv in old.items():
+                        if vv is None:
+                            os.environ.pop(kk, None)
+                        else:
+                            os.environ[kk] = vv
+                tm = {kk: round(v, 3) for kk, v in gficf_b200.last_timings().items()}
+                return dt, tm, gficf_b200.last_output()
+
             r_host = gficf_b200.pinned_empty((n, k))
-            r_host[...] = synth.to_r_matrix(idx0)
+            r_host[...] = r_host_matrix
             out_host = gficf_b200.pinned_empty((E, 3))
-            for _ in range(2):
-                gficf_b200.rcpp_parallel_jaccard_coef(r_host, False, 1, out=out_host)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                gficf_b200.rcpp_parallel_jaccard_coef(r_host, False, 1, out=out_host)
-            dt = (time.perf_counter() - t0) / e2e_steps
-            tm = gficf_b200.last_timings()
-            e2e = {"value": E / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": 24 * E,
-                   "ms_per_step": dt * 1e3, "call": "gficf_b200.rcpp_parallel_jaccard_coef (pinned host buffers)",
-                   "breakdown_ms": {kk: round(v, 3) for kk, v in tm.items() if kk != "reserved"}}
-            # the same call on ordinary pageable memory (what R hands over): staged through pinned slots
+            gficf_b200.rcpp_parallel_jaccard_coef(r_host, False, 1, out=out_host)
+            dt, tm, om = timed_call(r_host, out_host, e2e_steps)
+            e2e = {"value": E / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": int(om["d2h_bytes"]),
+                   "ms_per_step": dt * 1e3, "call": "gficf_b200.rcpp_parallel_jaccard_coef (f64 R matrix, pinned host buffers)",
+                   "output_mode": om, "breakdown_ms": tm}
+            if parity is not None:
+                oh = np.asarray(out_host)
+                parity["e2e_equals_oracle"] = rows_equal(chk, r_host_matrix, k, parity["oracle_rows"],
+                                                         lambda lo_, hi_: oh[lo_ * k:hi_ * k])
+                dev_res = out.cpu().numpy().T
+                parity["e2e_equals_value_path_full_matrix"] = bool(np.array_equal(oh, dev_res))
+                del dev_res
+            # r01's output path for comparison: the device writes 24 B/edge, the copy engine moves them
+            dtd, tmd, omd = timed_call(r_host, out_host, 3, {"GFICF_CUDA_OUT_MODE": "dma"})
+            e2e["dma_output_mode"] = {"value": E / dtd, "ms_per_step": dtd * 1e3, "d2h_bytes_per_step": int(omd["d2h_bytes"]),
+                                      "breakdown_ms": tmd}
+            # the same call on ordinary pageable memory (what R hands over)
             r_page = np.asfortranarray(np.array(r_host))
             out_page = np.zeros((E, 3), dtype=np.float64, order="F")
-            gficf_b200.rcpp_parallel_jaccard_coef(r_page, False, 1, out=out_page)
-            t0 = time.perf_counter()
-            for _ in range(3):
-                gficf_b200.rcpp_parallel_jaccard_coef(r_page, False, 1, out=out_page)
-            dtp = (time.perf_counter() - t0) / 3
-            e2e["pageable"] = {"value": E / dtp, "ms_per_step": dtp * 1e3,
-                               "matches_pinned": bool(np.array_equal(out_page[: 10**6], np.asarray(out_host)[: 10**6])
-                                                      and np.array_equal(out_page[-10**6:], np.asarray(out_host)[-10**6:])),
-                               "breakdown_ms": {kk: round(v, 3) for kk, v in gficf_b200.last_timings().items()
-                                                if kk != "reserved"}}
+            dtp, tmp_, omp = timed_call(r_page, out_page, 3)
+            e2e["pageable"] = {"value": E / dtp, "ms_per_step": dtp * 1e3, "output_mode": omp,
+                               "matches_pinned": bool(np.array_equal(out_page, np.asarray(out_host))),
+                               "breakdown_ms": tmp_}
             del r_page, out_page
             # uwot's integer matrix taken as it is (gficf_cuda_jaccard_i32): half the H2D bytes
             r_i32 = gficf_b200.pinned_empty((n, k), dtype=np.int32)
             r_i32[...] = np.asarray(r_host).astype(np.int32)
-            gficf_b200.rcpp_parallel_jaccard_coef(r_i32, False, 1, out=out_host)
-            t0 = time.perf_counter()
-            for _ in range(3):
-                gficf_b200.rcpp_parallel_jaccard_coef(r_i32, False, 1, out=out_host)
-            dti = (time.perf_counter() - t0) / 3
-            e2e["int32_input"] = {"value": E / dti, "ms_per_step": dti * 1e3, "h2d_bytes_per_step": 4 * E}
-            del r_i32
+            dti, tmi, omi = timed_call(r_i32, out_host, 3)
+            e2e["int32_input"] = {"value": E / dti, "ms_per_step": dti * 1e3, "h2d_bytes_per_step": 4 * E,
+                                  "d2h_bytes_per_step": int(omi["d2h_bytes"]), "output_mode": omi, "breakdown_ms": tmi}
+            del r_i32, r_host, out_host
         else:
             # one process per GPU on SHARED host matrices: every rank moves its own rows over its
             # own PCIe link (gficf_cuda_jaccard_rank); rank 0 owns / fills / checks the matrices
@@ -401,8 +551,6 @@ def run_ours(a):
             multiproc.comm_init_from_torch()
             tag = [("gficf_bench_%d_%d" % (os.getpid(), int(time.time()))) if rank == 0 else None]
             dist.broadcast_object_list(tag, src=0)
-            # NUMA: every rank runs on the CPUs next to its GPU and first-touches the rows it will
-            # move, so the D2H streams of 8 GPUs do not all land on one socket's memory
             numa = multiproc.bind_to_gpu_numa_node(local)
             numa_aware = numa.startswith("node")  # only then is first-touch placement meaningful
             r_sh = out_sh = None
@@ -410,7 +558,7 @@ def run_ours(a):
                 r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=True, pin=not numa_aware)
                 out_sh = multiproc.SharedHostMatrix(tag[0] + "_out", (E, 3), create=True, pin=not numa_aware)
                 if not numa_aware:
-                    r_sh.array[...] = synth.to_r_matrix(idx0)
+                    r_sh.array[...] = r_host_matrix if r_host_matrix is not None else synth.to_r_matrix(idx0)
             dist.barrier()
             if rank != 0:
                 r_sh = multiproc.SharedHostMatrix(tag[0] + "_idx", (n, k), create=False, pin=not numa_aware)
@@ -421,7 +569,7 @@ def run_ours(a):
                 out_sh.first_touch_rows(s_lo * k, s_hi * k)
                 dist.barrier()
                 if rank == 0:
-                    r_sh.array[...] = synth.to_r_matrix(idx0)
+                    r_sh.array[...] = r_host_matrix if r_host_matrix is not None else synth.to_r_matrix(idx0)
                 dist.barrier()
                 r_sh.pin()
                 out_sh.pin()
@@ -435,18 +583,25 @@ def run_ours(a):
             barrier()
             dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            om = gficf_b200.last_output()
+            d2h = torch.tensor([om["d2h_bytes"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(d2h)
             e2e = {"value": E / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": 8 * E,
-                   "d2h_bytes_per_step": 24 * E, "ms_per_step": float(dt[0]) * 1e3,
+                   "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": float(dt[0]) * 1e3,
                    "call": "gficf_b200.multiproc.rcpp_parallel_jaccard_coef_rank (one rank per GPU, shared "
                            "page-locked host matrices; each rank moves its own row slab)",
                    "pinned": bool(r_sh.pinned and out_sh.pinned), "numa_binding_rank0": numa,
-                   "breakdown_ms_rank0": {kk: round(v, 3) for kk, v in gficf_b200.last_timings().items()
-                                          if kk != "reserved"}}
-            if rank == 0:
-                # the shared result must be the single-GPU result
-                chk = out[:, : 3000 * k].cpu().numpy().T
-                e2e["matches_device_path_on_sample"] = bool(np.array_equal(out_sh.array[: 3000 * k], chk)) and \
-                    bool(np.array_equal(out_sh.array[E - 3000 * k:], out[:, E - 3000 * k:].cpu().numpy().T))
+                   "output_mode_rank0": om,
+                   "breakdown_ms_rank0": {kk: round(v, 3) for kk, v in gficf_b200.last_timings().items()}}
+            if rank == 0 and parity is not None:
+                parity["e2e_equals_oracle"] = rows_equal(chk, r_host_matrix, k, parity["oracle_rows"],
+                                                         lambda lo_, hi_: out_sh.array[lo_ * k:hi_ * k])
+                ok = True  # and the whole shared result against the value path, in pieces (host RAM)
+                step_e = 8_000_000
+                for e0_ in range(0, E, step_e):
+                    e1_ = min(E, e0_ + step_e)
+                    ok = ok and bool(np.array_equal(out_sh.array[e0_:e1_], out[:, e0_:e1_].cpu().numpy().T))
+                parity["e2e_equals_value_path_full_matrix"] = ok
             barrier()
             r_sh.close()
             out_sh.close()
@@ -476,67 +631,77 @@ def run_ours(a):
         except Exception as ex:  # an extra record, never a reason to lose the bench line
             snn_rec = {"error": str(ex)[:200]}
 
-    # ---- CPU baseline beside it (rank 0, N=1 only)
-    cpu = None
+    # ---- CPU baseline beside it (rank 0, N=1 only): all host threads, and nt=2 (the clustcells default)
+    cpu = cpu_nt2 = None
     if world == 1 and not a.no_cpu_baseline:
-        r = synth.to_r_matrix(idx0)
+        r = r_host_matrix if r_host_matrix is not None else synth.to_r_matrix(idx0)
         run, m, kind, cores = reference_sampler(r, k, a.cpu_seconds)
         t = run(0, m)
         cpu = {"value": m * k / t, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": "rows [0,%d) of %d (%.3g edges) gathering from the full matrix, %.1f s" % (m, n, m * k, t)}
-        # and the GPU result of those rows must be what the reference computed
-        ref_rows = min(m, 2000)
-        from oracle.binding import Reference, Oracle
-        chk = (Reference() if Reference.available() else Oracle()).parallel_rows(r, 0, ref_rows)
-        got = out[:, : ref_rows * k].cpu().numpy().T
-        cpu["gpu_matches_on_sample"] = bool(np.array_equal(got, chk))
+        if parity is not None:
+            cpu["gpu_matches_on_sample"] = parity["value_path_equals_oracle"]
+        run2, m2, kind2, _ = reference_sampler(r, k, min(6.0, a.cpu_seconds), nthreads=2)
+        t2 = run2(0, m2)
+        cpu_nt2 = {"value": m2 * k / t2, "unit": UNIT, "cores": 2, "kind": kind2,
+                   "what": "RcppParallel::setThreadOptions(numThreads = nt), nt = 2: the clustcells() default "
+                           "(R/clustCells.R:46,64)",
+                   "sample": "rows [0,%d) of %d (%.3g edges), %.1f s" % (m2, n, m2 * k, t2)}
 
-    traffic = None
-    try:  # ncu-measured DRAM bytes per launch of this exact kernel/workload, if a capture was committed
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        key = ("jaccard_small_k_kernel<32,false>" if 16 < k <= 32 else "jaccard_wide_k_kernel<false>") + \
-            " cells=%d k=%d" % (n, k)
-        if world == 1 and key in tj:
-            traffic = tj[key]["traffic_bytes"]
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    if rank == 0 and world == 1:
+        if not a.no_traffic_probe:
+            del out
+            torch.cuda.empty_cache()
+            traffic, traffic_src = probe_traffic(a)
+        if traffic is None:
+            try:  # committed ncu capture of this exact kernel/workload
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+                key = "cells=%d k=%d" % (n, k)
+                if key in tj:
+                    traffic, traffic_src = tj[key]["traffic_bytes"], "profiles/r02_traffic.json (%s); live probe: %s" % (
+                        tj[key].get("from", "ncu --set full"), traffic_src)
+            except Exception:
+                pass
     if rank == 0:
         g, b, s, v = (C_int32() for _ in range(4))
         gficf_b200.lib().gficf_cuda_last_launch(g, b, s, v)
+        if world == 1:
+            kname = ("jaccard_small_k_kernel<%d,0>" % D.row_stride(k)) if k <= 32 else \
+                ("jaccard_wide_k_kernel<0>" if k <= 128 else "jaccard_large_k_kernel")
+        else:
+            kname = ("jaccard_small_k_kernel<%d,1>" % D.row_stride(k)) if k <= 32 else \
+                ("jaccard_wide_k_kernel<1>" if k <= 128 else "jaccard_large_k_kernel")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 ids / f64 weights", "data": "synthetic",
-            "config": {"workload": workload_name(a), "cells": n, "k": k, "edges": E,
-                       "l2": "explicit 256 MiB flush write between timed steps; index 4*n*32 B = %.0f MB > 126 MB L2"
-                             % (n * 32 * 4 / 1e6),
-                       "sharding": "none" if world == 1 else
-                       "rows over %d ranks, host rank takes %.1f%% (expand/count cost ratio %.3f measured); resident "
-                       "replicated int32 index; %d chunks per rank; u8 counts reach rank 0 %s; expand kernel on rank 0 "
-                       "overlapping the next chunk" % (
-                           world, 100.0 * host_share, rho, a.chunks,
-                           "by peer stores from the count kernel's epilogue (CUDA IPC mapping over NVLink, flag per "
-                           "chunk)" if a.gather == "peer" else "over NCCL send/recv as counted"),
+            "config": {"workload": workload_name(a), "config": a.config, "cells": n, "k": k, "edges": E,
+                       "l2": "explicit 256 MiB flush write between timed steps; index %d*n*4 B = %.0f MB vs 126 MB L2"
+                             % (D.row_stride(k), n * D.row_stride(k) * 4 / 1e6),
+                       "sharding": sharding_note,
                        "launch": {"grid": g.value, "block": b.value, "smem": s.value}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic,
-                         "kernel": ("jaccard_small_k_kernel<%d,%s>" % (D.row_stride(k), "false" if world == 1 else "true")) if k <= 32
-                         else ("jaccard_wide_k_kernel<%s>" % ("false" if world == 1 else "true")),
-                         "bytes_per_edge": bpe, "edges_per_launch": edges_per_launch,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": kname, "bytes_per_edge": bpe, "edges_per_launch": edges_per_launch,
                          "kernel_ms": kern_avg_ms, "peak_source": peak_src},
             "kernel_only": None if world == 1 else {
                 "value": E / (kern_avg_ms * 1e-3), "unit": UNIT, "ms": kern_avg_ms,
                 "what": "all ranks counting their rows concurrently, slowest rank's kernel; no gather / expand"},
             "clocks": clocks,
-            "gpu_launches": launches_per_step * a.steps if world == 1 else int(total_launches * a.steps / (a.steps + max(3, a.warmup))),
+            "gpu_launches": a.steps if world == 1 else int(total_launches),
             "loop_wall_ms": t_wall * 1e3,
         }
+        if parity:
+            line["parity"] = parity
         if snn_rec:
             line["snn_next_row"] = snn_rec
         if e2e:
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if cpu_nt2:
+            line["cpu_baseline_nt2"] = cpu_nt2
         print(json.dumps(line))
     if world > 1:
         if a.gather == "peer":
@@ -557,7 +722,9 @@ def main():
     real = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     sys.stdout = real
-    if a.impl == "reference":
+    if a.traffic_probe:
+        run_traffic_probe(a)
+    elif a.impl == "reference":
         run_reference_arm(a)
     else:
         run_ours(a)

@@ -20,6 +20,7 @@ from .api import (  # noqa: F401
     MODE_PARALLEL,
     MODE_SERIAL,
     jaccard_coeff,
+    last_output,
     last_timings,
     phenograph_edges,
     pinned_empty,
@@ -30,5 +31,5 @@ from .api import (  # noqa: F401
 __all__ = [
     "GficfCudaError", "build", "lib", "library_path", "MODE_PARALLEL", "MODE_SERIAL",
     "jaccard_coeff", "rcpp_parallel_jaccard_coef", "phenograph_edges", "pinned_empty",
-    "set_devices", "last_timings",
+    "set_devices", "last_timings", "last_output",
 ]

@@ -30,6 +30,9 @@ PROTOTYPES = {
     "gficf_cuda_host_unregister": (C.c_int, [_vp]),
     "gficf_cuda_release": (C.c_int, []),
     "gficf_cuda_last_timings": (C.c_int, [_dp]),
+    "gficf_cuda_last_output": (C.c_int, [C.POINTER(C.c_int32), _dp, _dp]),
+    "gficf_cuda_expand_host": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int32, _vp, C.c_int64, C.c_int64, _vp,
+                                         C.c_int32]),
     "gficf_cuda_comm_unique_id": (C.c_int, [_vp]),
     "gficf_cuda_comm_init_rank": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_size_t]),
     "gficf_cuda_comm_destroy": (C.c_int, []),
@@ -42,6 +45,10 @@ PROTOTYPES = {
     "gficf_cuda_wait_dev": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "gficf_cuda_expand_wait_dev": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp,
                                              C.c_int32, C.c_uint32, C.c_int64, _vp, _vp]),
+    "gficf_cuda_jaccard_counts_tagged_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _vp,
+                                                       C.c_uint32, _vp, _vp]),
+    "gficf_cuda_expand_stream_dev": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                               C.c_int32, _vp, _vp, _vp, _vp, C.c_uint32, C.c_int64, _vp, _vp]),
     "gficf_cuda_row_stride": (C.c_int32, [C.c_int32]),
     "gficf_cuda_layout_dev": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64,
                                         C.c_int64, _vp, _vp, _vp]),

@@ -128,5 +128,14 @@ def set_devices(n: int) -> None:
 def last_timings() -> dict:
     buf = (C.c_double * 8)()
     _lib.check(_lib.lib().gficf_cuda_last_timings(buf))
-    keys = ["h2d_ms", "layout_ms", "jaccard_ms", "d2h_ms", "wall_ms", "allgather_ms", "launches", "reserved"]
+    keys = ["h2d_ms", "layout_ms", "jaccard_ms", "d2h_ms", "wall_ms", "allgather_ms", "launches", "d2h_bytes"]
     return dict(zip(keys, list(buf)))
+
+
+def last_output() -> dict:
+    """How the last host-buffer call produced its output columns (include/gficf_cuda.h,
+    gficf_cuda_last_output): mode dma / host / hybrid, share written by host threads, PCIe bytes."""
+    mode, share, nbytes = C.c_int32(0), C.c_double(0), C.c_double(0)
+    _lib.check(_lib.lib().gficf_cuda_last_output(C.byref(mode), C.byref(share), C.byref(nbytes)))
+    return {"mode": {1: "dma", 2: "host", 3: "hybrid"}.get(mode.value, str(mode.value)),
+            "host_share": share.value, "d2h_bytes": nbytes.value}

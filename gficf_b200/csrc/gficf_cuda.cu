@@ -5,7 +5,7 @@
 // Replaces the bodies of rcpp_parallel_jaccard_coef
 // (reference src/rcpp_parallel_jaccard_coeff.cpp:58-80) and jaccard_coeff
 // (src/jaccard_coeff.cpp:19-45).  There is deliberately no CPU fallback.
-#include "../../include/gficf_cuda.h"
+#include "gficf_cuda.h"  // include/gficf_cuda.h (-I)
 
 #include <cuda_runtime.h>
 #if defined(__x86_64__)
@@ -24,6 +24,7 @@
 #include <thread>
 #include <vector>
 
+#include "host_expand.h"
 #include "jaccard_kernels.cuh"
 #include "snn_kernels.cuh"
 #include "nccl_dyn.h"
@@ -77,6 +78,11 @@ struct LaunchInfo {
 };
 thread_local LaunchInfo tl_launch;
 thread_local double tl_timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+struct OutputInfo {
+  int mode = 1;           // OutMode of the last host-buffer call
+  double host_share = 0;  // share of the output pieces written by host threads
+};
+thread_local OutputInfo tl_output;
 
 struct DevProps {
   bool ok = false;
@@ -131,11 +137,11 @@ int persistent_grid(K kernel, int block, size_t smem, long long work_ctas) {
 
 template <int KP, int CO, bool SKIP>
 void launch_small_t(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
-                    uint8_t* u, unsigned* flags, cudaStream_t st) {
+                    uint8_t* u, unsigned* flags, cudaStream_t st, unsigned tag) {
   auto kern = jaccard_small_k_kernel<KP, CO, SKIP>;
   const int block = kSmallWarps * 32;
   const int grid = persistent_grid(kern, block, 0, (hi - lo + kSmallWarps - 1) / kSmallWarps);
-  kern<<<grid, block, 0, st>>>(idx, k, lo, hi, f, t, w, u, flags);
+  kern<<<grid, block, 0, st>>>(idx, k, lo, hi, f, t, w, u, flags, tag);
   tl_launch = {grid, block, (int)(sizeof(unsigned) * kSmallWarps * SmallK<KP>::TS + 33 * 8), KP};
 }
 
@@ -143,14 +149,14 @@ void launch_small_t(const int* idx, int k, long long lo, long long hi, double* f
 // row is padding (k <= KP-4, e.g. k=25..28 in 32-int rows); k=30 keeps the lean variant
 template <int KP, int CO>
 void launch_small(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
-                  uint8_t* u, unsigned* flags, cudaStream_t st) {
-  if (KP > 4 && k <= KP - 4) launch_small_t<KP, CO, true>(idx, k, lo, hi, f, t, w, u, flags, st);
-  else launch_small_t<KP, CO, false>(idx, k, lo, hi, f, t, w, u, flags, st);
+                  uint8_t* u, unsigned* flags, cudaStream_t st, unsigned tag) {
+  if (KP > 4 && k <= KP - 4) launch_small_t<KP, CO, true>(idx, k, lo, hi, f, t, w, u, flags, st, tag);
+  else launch_small_t<KP, CO, false>(idx, k, lo, hi, f, t, w, u, flags, st, tag);
 }
 
 template <int LOG_TS, int CO>
 void launch_wide(const int* idx, int k, int kp, long long lo, long long hi, double* f, double* t,
-                 double* w, uint8_t* u, unsigned* flags, cudaStream_t st) {
+                 double* w, uint8_t* u, unsigned* flags, cudaStream_t st, unsigned tag) {
   auto kern = jaccard_wide_k_kernel<LOG_TS, CO>;
   const size_t smem = wide_smem_bytes(LOG_TS);
   static thread_local bool attr_set[64] = {};
@@ -162,7 +168,7 @@ void launch_wide(const int* idx, int k, int kp, long long lo, long long hi, doub
   }
   const int block = kWideWarps * 32;
   const int grid = persistent_grid(kern, block, smem, hi - lo);
-  kern<<<grid, block, smem, st>>>(idx, k, kp, lo, hi, f, t, w, u, flags);
+  kern<<<grid, block, smem, st>>>(idx, k, kp, lo, hi, f, t, w, u, flags, tag);
   tl_launch = {grid, block, (int)smem, 1000 + LOG_TS};
 }
 
@@ -196,21 +202,22 @@ void launch_large(const int* idx, int k, int kp, long long lo, long long hi, dou
 // 1 = counts, 2 = counts with the mutual-neighbour bit (k <= 127)
 template <int CO>
 bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, double* t, double* w,
-                 void* u_any, unsigned* flags, cudaStream_t st) {
+                 void* u_any, unsigned* flags, cudaStream_t st, unsigned tag = 0) {
   uint8_t* u = (uint8_t*)u_any;  // one byte per edge for k <= 255, two above
   if (CO == 2 && k > 127) return false;  // bit 7 of the count byte carries the mutual flag
+  if (tag && (CO != 1 || k > 127)) return false;  // ... or the epoch bit of the streaming gather
   if (hi <= lo) return true;
   const int kp = row_stride(k);
-  if (k <= 4) launch_small<4, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
-  else if (k <= 8) launch_small<8, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
-  else if (k <= 16) launch_small<16, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
-  else if (k <= 32) launch_small<32, CO>(idx, k, lo, hi, f, t, w, u, flags, st);
+  if (k <= 4) launch_small<4, CO>(idx, k, lo, hi, f, t, w, u, flags, st, tag);
+  else if (k <= 8) launch_small<8, CO>(idx, k, lo, hi, f, t, w, u, flags, st, tag);
+  else if (k <= 16) launch_small<16, CO>(idx, k, lo, hi, f, t, w, u, flags, st, tag);
+  else if (k <= 32) launch_small<32, CO>(idx, k, lo, hi, f, t, w, u, flags, st, tag);
   else if (k <= 128) {
     switch (wide_log_ts(k)) {
-      case 10: launch_wide<10, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
-      case 11: launch_wide<11, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
-      case 12: launch_wide<12, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
-      default: launch_wide<13, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st); break;
+      case 10: launch_wide<10, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st, tag); break;
+      case 11: launch_wide<11, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st, tag); break;
+      case 12: launch_wide<12, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st, tag); break;
+      default: launch_wide<13, CO>(idx, k, kp, lo, hi, f, t, w, u, flags, st, tag); break;
     }
   } else if (k <= kLargeMaxK) {
     if (CO == 2) return false;
@@ -220,6 +227,19 @@ bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, d
   }
   CU_TRY(cudaGetLastError());
   return true;
+}
+
+// bounded spins of the peer-memory kernels: GFICF_CUDA_PEER_TIMEOUT_MS (default 20 s) in SM clocks
+long long peer_spin_clocks(long long timeout_ms) {
+  if (timeout_ms <= 0) {
+    const char* e = getenv("GFICF_CUDA_PEER_TIMEOUT_MS");
+    timeout_ms = e ? atoll(e) : 0;
+    if (timeout_ms <= 0) timeout_ms = 20000;
+  }
+  int dev = 0, khz = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+  return timeout_ms * (long long)khz;
 }
 
 int grid_1d(long long total, int block, int cap_per_sm = 8) {
@@ -273,7 +293,7 @@ void launch_expand_t(const int* idx, int k, long long lo, long long hi, const CT
   if (total <= 0) return;
   if (mode == GFICF_MODE_PARALLEL) {
     expand_fixed_kernel<CT><<<grid_1d(total, kExpandThreads, 8), kExpandThreads, 0, st>>>(
-        idx, k, kp, lo, hi, d_u, f, t, w, nullptr, 0, 0u, 0, nullptr);
+        idx, k, kp, lo, hi, d_u, f, t, w, nullptr, 0, 0u, 0, nullptr, 0);
   } else {
     long long* chunk = (long long*)scratch;
     const long long nchunks = (total + kCompactChunk - 1) / kCompactChunk;
@@ -346,7 +366,8 @@ struct DeviceWs {
   cudaEvent_t ev_k0[kMaxChunks] = {}, ev_k1[kMaxChunks] = {};
   // in_raw: device copy of the caller's rows (f64 or int32, column-major); small: flags + n_written
   Buf in_raw, idx, out, counts, scratch, small;
-  PinBuf ring;
+  PinBuf ring, h_counts;  // h_counts: the slab's 1-byte counts on the host (counts-over-PCIe output mode)
+  cudaEvent_t ev_cnt_done = nullptr, ev_exp = nullptr, ev_dma[4] = {};
   cudaEvent_t ev_slot[kStageSlots] = {};
   unsigned* h_small = nullptr;  // pinned mirror of `small`
 
@@ -361,6 +382,9 @@ struct DeviceWs {
     for (auto& e : ev_k0) CU_TRY(cudaEventCreate(&e));
     for (auto& e : ev_k1) CU_TRY(cudaEventCreate(&e));
     for (auto& e : ev_slot) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ev_dma) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ev_cnt_done, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ev_exp, cudaEventDisableTiming));
     small.need(64);
     CU_TRY(cudaHostAlloc((void**)&h_small, 64, cudaHostAllocDefault));
     init = true;
@@ -371,6 +395,10 @@ struct DeviceWs {
     cudaDeviceSynchronize();
     in_raw.drop(); idx.drop(); out.drop(); counts.drop(); scratch.drop(); small.drop();
     ring.drop();
+    h_counts.drop();
+    cudaEventDestroy(ev_cnt_done);
+    cudaEventDestroy(ev_exp);
+    for (auto& e : ev_dma) cudaEventDestroy(e);
     if (h_small) cudaFreeHost(h_small);
     h_small = nullptr;
     for (auto& e : ev) cudaEventDestroy(e);
@@ -394,6 +422,8 @@ struct NcclState {
   ncclComm_t comms[kMaxDevices] = {};
 } g_nccl;
 
+std::atomic<int> g_sharers{1};  // ranks on this host (one process per GPU); they share its cores
+
 // one process per GPU: the communicator built from a unique id the host framework distributes
 struct MpState {
   ncclComm_t comm = nullptr;
@@ -403,6 +433,7 @@ struct MpState {
 void mp_release() {
   if (g_mp.comm) nccl_dyn::get().CommDestroy(g_mp.comm);
   g_mp = MpState();
+  g_sharers.store(1);
 }
 
 void nccl_release() {
@@ -464,37 +495,35 @@ int copy_threads() {
 
 // Device -> pageable host: the destination will not be read again soon, so the pieces are written
 // with non-temporal stores (no read-for-ownership of the destination lines).
-void copy_out(char* dst, const char* src, size_t bytes) {
-#if defined(__x86_64__) && defined(__SSE2__)
-  if (bytes >= 4096 && (((uintptr_t)dst ^ (uintptr_t)src) & 7) == 0) {
-    while (((uintptr_t)dst & 15) && bytes >= 8) {
-      memcpy(dst, src, 8);
-      dst += 8;
-      src += 8;
-      bytes -= 8;
-    }
-    if (((uintptr_t)dst & 15) == 0) {
-      const size_t blocks = bytes / 64;
-      const __m128i* s = (const __m128i*)src;
-      __m128i* d = (__m128i*)dst;
-      for (size_t b = 0; b < blocks; ++b) {
-        const __m128i x0 = _mm_loadu_si128(s + 0), x1 = _mm_loadu_si128(s + 1);
-        const __m128i x2 = _mm_loadu_si128(s + 2), x3 = _mm_loadu_si128(s + 3);
-        _mm_stream_si128(d + 0, x0);
-        _mm_stream_si128(d + 1, x1);
-        _mm_stream_si128(d + 2, x2);
-        _mm_stream_si128(d + 3, x3);
-        s += 4;
-        d += 4;
-      }
-      _mm_sfence();
-      dst += blocks * 64;
-      src += blocks * 64;
-      bytes -= blocks * 64;
-    }
-  }
-#endif
-  if (bytes) memcpy(dst, src, bytes);
+void copy_out(char* dst, const char* src, size_t bytes) { gficf_host::stream_copy(dst, src, bytes); }
+
+// Threads that write the output columns from the 1-byte counts (counts-over-PCIe output mode).
+// The devices / ranks of one call share the host's cores.
+int expand_threads() {
+  static int t = [] {
+    const char* e = getenv("GFICF_CUDA_EXPAND_THREADS");
+    int v = e ? atoi(e) : 0;
+    if (v <= 0) v = std::max(2, std::min(32, (int)std::thread::hardware_concurrency() - 2));
+    return v;
+  }();
+  return std::max(1, t / std::max(1, g_active_devices.load() * g_sharers.load()));
+}
+
+// How the (n*k) x 3 doubles of the parallel export reach the caller's matrix:
+//   dma     the device writes all 24 B/edge and the copy engine moves them (r01 path)
+//   host    only the 1-byte counts cross PCIe; host threads write the three columns (host_expand.h)
+//   hybrid  both at once: (column, row-chunk) pieces are claimed from one list, the host threads from
+//           the end that is cheapest for them (from, weight), the copy engine from the other (to)
+//   auto    hybrid when the output buffer is page-locked, host when it is pageable (what R passes:
+//           a staged DMA would cost the host a 24 B/edge read AND write), dma when k > 255
+enum OutMode { kOutAuto = 0, kOutDma, kOutHost, kOutHybrid };
+OutMode out_mode_env() {
+  const char* e = getenv("GFICF_CUDA_OUT_MODE");
+  if (!e) return kOutAuto;
+  if (!strcmp(e, "dma")) return kOutDma;
+  if (!strcmp(e, "host")) return kOutHost;
+  if (!strcmp(e, "hybrid")) return kOutHybrid;
+  return kOutAuto;
 }
 
 struct Piece {
@@ -563,19 +592,23 @@ void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cud
     const Piece& pc = pieces[j];
     char* slot = ring + (size_t)(j % kStageSlots) * kStageChunk;
     if (pc.wait_before) err = cudaStreamWaitEvent(st, pc.wait_before, 0);
+    // a worker that failed stops marking pieces: never wait for it (failed ends the loop below)
     if (to_device) {
-      while (!host_done[j].load(std::memory_order_acquire)) std::this_thread::yield();
+      while (!host_done[j].load(std::memory_order_acquire) && !failed.load()) std::this_thread::yield();
+      if (failed.load()) break;
       if (err == cudaSuccess) err = cudaMemcpyAsync(pc.dev, slot, pc.bytes, cudaMemcpyHostToDevice, st);
     } else {
       // the slot is free once piece j - kStageSlots has been copied out by a worker
       if (j >= kStageSlots)
-        while (!host_done[j - kStageSlots].load(std::memory_order_acquire)) std::this_thread::yield();
+        while (!host_done[j - kStageSlots].load(std::memory_order_acquire) && !failed.load())
+          std::this_thread::yield();
+      if (failed.load()) break;
       if (err == cudaSuccess) err = cudaMemcpyAsync(slot, pc.dev, pc.bytes, cudaMemcpyDeviceToHost, st);
     }
     if (err == cudaSuccess) err = cudaEventRecord(ws.ev_slot[j % kStageSlots], st);
     dma_issued[j].store(1, std::memory_order_release);
   }
-  if (err != cudaSuccess) {
+  if (err != cudaSuccess || failed.load()) {
     failed.store(true);
     for (int j = 0; j < np; ++j) {
       dma_issued[j].store(1);
@@ -629,6 +662,9 @@ struct SlabResult {
   long long n_written = -1;
   float ms_h2d = 0, ms_k0 = 0, ms_k1 = 0, ms_d2h = 0, ms_gather = 0;
   int launches = 0;
+  double d2h_bytes = 0;       // bytes that crossed PCIe towards the host
+  int out_mode = kOutDma;     // how the output columns were produced (OutMode)
+  double host_items = 0;      // share of the output pieces written by host threads
   bool counts_ready = false;  // phase 1 left fast-kernel counts in ws.counts
   Err err;
 };
@@ -640,6 +676,7 @@ struct Slab {
   long long n, rows_per, lo, hi, rows, E, slab_e;
   const void* h_idx;
   int elem = 8;  // bytes per element of the caller's matrix: 8 = double, 4 = int32
+  int out_mode = kOutDma;  // resolved OutMode of this call (never kOutAuto)
   double* h_out;
   Slab(int rank_, int ndev_, const void* h_idx_, long long n_, int k_, long long rows_per_,
        double* h_out_, int mode_)
@@ -677,6 +714,78 @@ void d2h_slab(DeviceWs& ws, const Slab& s, SlabResult* res) {
   res->ms_d2h += ms;
 }
 
+// Counts-over-PCIe output of the parallel export (modes host / hybrid, see OutMode).
+// On entry: ws.counts holds the slab's 1-byte counts and their D2H into ws.h_counts is in flight on
+// s_copy (ev_cnt_done behind it); with use_dma, ws.out holds the expanded doubles (ev_exp on s_comp).
+// The slab's output is cut into (column, row-chunk) pieces kept in ONE list ordered by what the host
+// threads do cheapest: from (no input read), weight (table lookup), to (transposed read of the
+// caller's matrix).  Host threads claim from the front, the copy engine from the back; the call is
+// over when the two ends meet -- the split adapts to whatever the host's memory system and the
+// PCIe link deliver, nothing is calibrated.
+void counts_output_phase(DeviceWs& ws, const Slab& s, SlabResult* res, bool use_dma) {
+  const int k = s.k;
+  const long long rows_per_piece = std::max<long long>(256, (6ll << 20) / (8ll * k));
+  const long long nc = (s.rows + rows_per_piece - 1) / rows_per_piece;
+  const long long nitems = 3 * nc;
+  static const int kCpuOrder[3] = {0, 2, 1};
+  std::atomic<unsigned long long> ends((unsigned long long)nitems);  // front in the high 32 bits, back in the low
+  auto claim = [&](bool front, long long* item) {
+    unsigned long long v = ends.load();
+    for (;;) {
+      const unsigned long long lo = v >> 32, hi = v & 0xffffffffull;
+      if (lo >= hi) return false;
+      const unsigned long long nv = front ? (((lo + 1) << 32) | hi) : ((lo << 32) | (hi - 1));
+      if (ends.compare_exchange_weak(v, nv)) {
+        *item = (long long)(front ? lo : hi - 1);
+        return true;
+      }
+    }
+  };
+  double lut[256];
+  gficf_host::fill_weight_table(k, lut);
+  gficf_host::ExpandJob job{s.h_idx, s.elem, s.n, k, (const uint8_t*)ws.h_counts.p, s.lo, s.h_out, s.E, lut};
+  CU_TRY(cudaEventSynchronize(ws.ev_cnt_done));  // the counts are on the host
+  const int nthreads = (int)std::min<long long>(expand_threads(), nitems);
+  std::vector<std::thread> pool;
+  std::atomic<long long> cpu_items(0);
+  for (int t = 0; t < nthreads; ++t)
+    pool.emplace_back([&] {
+      long long it;
+      while (claim(true, &it)) {
+        const int col = kCpuOrder[it / nc];
+        const long long a = (it % nc) * rows_per_piece, b = std::min(s.rows, a + rows_per_piece);
+        gficf_host::expand_column(job, col, s.lo + a, s.lo + b);
+        cpu_items.fetch_add(1);
+      }
+    });
+  cudaError_t err = cudaSuccess;
+  long long dma_items = 0;
+  if (use_dma) {
+    const double* d_out = (const double*)ws.out.p;
+    err = cudaStreamWaitEvent(ws.s_copy, ws.ev_exp, 0);
+    long long it;
+    // at most 3 copies queued: the copy engine never idles, and it never claims far ahead of what it moves
+    while (err == cudaSuccess && claim(false, &it)) {
+      const int col = kCpuOrder[it / nc];
+      const long long a = (it % nc) * rows_per_piece, b = std::min(s.rows, a + rows_per_piece);
+      const size_t bytes = (size_t)(b - a) * k * sizeof(double);
+      if (dma_items >= 3) err = cudaEventSynchronize(ws.ev_dma[(dma_items - 3) & 3]);
+      if (err == cudaSuccess)
+        err = cudaMemcpyAsync(s.h_out + (size_t)col * s.E + (size_t)(s.lo + a) * k,
+                              d_out + (size_t)col * s.slab_e + (size_t)a * k, bytes, cudaMemcpyDeviceToHost,
+                              ws.s_copy);
+      if (err == cudaSuccess) err = cudaEventRecord(ws.ev_dma[dma_items & 3], ws.s_copy);
+      res->d2h_bytes += (double)bytes;
+      ++dma_items;
+    }
+  }
+  for (auto& t : pool) t.join();
+  if (err == cudaSuccess) err = cudaStreamSynchronize(ws.s_copy);
+  if (err != cudaSuccess) throw Err{GFICF_E_CUDA, fmt("output copy failed: %s", cudaGetErrorString(err))};
+  res->out_mode = use_dma ? kOutHybrid : kOutHost;
+  res->host_items = (double)cpu_items.load() / (double)std::max<long long>(1, nitems);
+}
+
 // Phase 1 of one device's share (rows [lo,hi) of n): H2D of its rows, layout pre-pass, exchange
 // of the int32 index slabs (in-place NCCL all-gather when ndev>1), then the fast kernel:
 //   parallel export, k<=128: fused kernel in row chunks, the D2H of chunk c overlapping the
@@ -694,11 +803,13 @@ void device_phase0(Slab s, SlabResult* res) {
     const int cbytes = k <= 255 ? 1 : 2;
     ws.in_raw.need(std::max<size_t>(16, (size_t)s.rows * k * s.elem));
     ws.idx.need(std::max<size_t>(16, (size_t)s.rows_per * s.ndev * s.kp * sizeof(int)));
-    ws.out.need(std::max<size_t>(16, (size_t)s.slab_e * 3 * sizeof(double)));
-    if (s.mode == GFICF_MODE_SERIAL || k > kLargeMaxK) {
+    if (s.out_mode != kOutHost) ws.out.need(std::max<size_t>(16, (size_t)s.slab_e * 3 * sizeof(double)));
+    if (s.mode == GFICF_MODE_SERIAL || k > kLargeMaxK || s.out_mode != kOutDma) {
       ws.counts.need(std::max<size_t>(16, (size_t)s.slab_e * cbytes));
       ws.scratch.need(expand_scratch_bytes(s.slab_e));
     }
+    if (s.out_mode != kOutDma) ws.h_counts.need(std::max<size_t>(16, (size_t)s.slab_e));
+    if (s.out_mode == kOutHost) ws.out.need(16);  // grown on demand should the exact path be needed
     unsigned* d_flags = (unsigned*)ws.small.p;
     CU_TRY(cudaMemsetAsync(ws.small.p, 0, 64, ws.s_comp));
     CU_TRY(cudaEventRecord(ws.ev[0], ws.s_comp));
@@ -738,6 +849,53 @@ void device_phase1(Slab s, SlabResult* res) {
     double* d_to = d_from + s.slab_e;
     double* d_w = d_to + s.slab_e;
     int used = 0;
+    if (fast_ok && s.mode == GFICF_MODE_PARALLEL && s.out_mode != kOutDma && s.slab_e > 0) {
+      // counts-over-PCIe: count kernel in row chunks, the D2H of chunk c's counts overlapping the
+      // kernel of chunk c+1; then the output phase (host threads [+ copy engine])
+      const bool use_dma = s.out_mode == kOutHybrid;
+      const int nch = (int)std::min<long long>(8, std::max<long long>(1, s.slab_e / (8ll << 20)));
+      const long long rpc = (s.rows + nch - 1) / nch;
+      uint8_t* d_cnt = (uint8_t*)ws.counts.p;
+      CU_TRY(cudaStreamWaitEvent(ws.s_copy, ws.ev[3], 0));
+      for (int c = 0; c < nch; ++c) {
+        const long long clo = s.lo + c * rpc, chi = std::min(s.hi, clo + rpc);
+        if (clo >= chi) break;
+        const long long eo = (clo - s.lo) * k;
+        CU_TRY(cudaEventRecord(ws.ev_k0[c], ws.s_comp));
+        launch_fast<1>(d_idx, k, clo, chi, nullptr, nullptr, nullptr, d_cnt + eo, d_flags, ws.s_comp);
+        CU_TRY(cudaEventRecord(ws.ev_k1[c], ws.s_comp));
+        CU_TRY(cudaEventRecord(ws.ev_chunk[c], ws.s_comp));
+        CU_TRY(cudaStreamWaitEvent(ws.s_copy, ws.ev_chunk[c], 0));
+        CU_TRY(cudaMemcpyAsync((char*)ws.h_counts.p + eo, d_cnt + eo, (size_t)(chi - clo) * k,
+                               cudaMemcpyDeviceToHost, ws.s_copy));
+        res->launches++;
+        used = c + 1;
+      }
+      CU_TRY(cudaEventRecord(ws.ev_cnt_done, ws.s_copy));
+      res->d2h_bytes += (double)s.slab_e;
+      if (use_dma) {
+        launch_expand(d_idx, k, s.lo, s.hi, d_cnt, GFICF_MODE_PARALLEL, d_from, d_to, d_w, nullptr, nullptr,
+                      ws.s_comp);
+        res->launches++;
+      }
+      CU_TRY(cudaEventRecord(ws.ev_exp, ws.s_comp));
+      read_small(ws, res);  // flags of the count kernels (waits for s_comp)
+      res->counts_ready = true;
+      const auto t_out0 = std::chrono::steady_clock::now();
+      if (!(res->flags & (kFlagBadId | kFlagDupId | kFlagHashFail)))
+        counts_output_phase(ws, s, res, use_dma);  // else: the exact path rewrites everything
+      res->ms_d2h = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_out0).count();
+      CU_TRY(cudaStreamSynchronize(ws.s_copy));
+      CU_TRY(cudaEventElapsedTime(&res->ms_h2d, ws.ev[0], ws.ev[1]));
+      CU_TRY(cudaEventElapsedTime(&res->ms_k0, ws.ev[1], ws.ev[2]));
+      CU_TRY(cudaEventElapsedTime(&res->ms_gather, ws.ev[2], ws.ev[3]));
+      for (int c = 0; c < used; ++c) {
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, ws.ev_k0[c], ws.ev_k1[c]));
+        res->ms_k1 += ms;
+      }
+      return;
+    }
     if (fast_ok && s.mode == GFICF_MODE_PARALLEL) {
       const int nch =
           (int)std::min<long long>(kMaxChunks, std::max<long long>(1, s.slab_e * 24 / (48ll << 20)));
@@ -766,6 +924,7 @@ void device_phase1(Slab s, SlabResult* res) {
         segs.push_back({(char*)(s.h_out + 2 * s.E + s.lo * k + eo), (char*)(d_w + eo), cb, nullptr});
       }
       d2h_segs(ws, segs, ws.s_copy);
+      res->d2h_bytes += 24.0 * (double)s.slab_e;
       CU_TRY(cudaEventRecord(ws.ev[5], ws.s_copy));
     } else if (fast_ok && s.slab_e > 0) {
       ws.counts.need(std::max<size_t>(16, (size_t)s.slab_e * cbytes));
@@ -803,6 +962,7 @@ void device_phase2(Slab s, bool exact, SlabResult* res) {
     const int k = s.k;
     const int cbytes = k <= 255 ? 1 : 2;
     const int* d_idx = (const int*)ws.idx.p;
+    ws.out.need(std::max<size_t>(16, (size_t)s.slab_e * 3 * sizeof(double)));  // host mode kept it empty
     double* d_from = (double*)ws.out.p;
     double* d_to = d_from + s.slab_e;
     double* d_w = d_to + s.slab_e;
@@ -827,6 +987,18 @@ void device_phase2(Slab s, bool exact, SlabResult* res) {
   } catch (const Err& e) {
     res->err = e;
   }
+}
+
+// OutMode of a host-buffer call (never kOutAuto): the counts-over-PCIe modes need 1-byte counts and
+// the fixed-slot export; the copy engine can only take part when the output buffer is page-locked
+int resolve_out_mode(const double* out, int k, int mode) {
+  if (mode != GFICF_MODE_PARALLEL || k > 255) return kOutDma;
+  OutMode m = out_mode_env();
+  if (m == kOutDma) return kOutDma;
+  const bool pinned = is_pinned(out);
+  if (m == kOutAuto) return pinned ? kOutHybrid : kOutHost;
+  if (m == kOutHybrid && !pinned) return kOutHost;
+  return m;
 }
 
 int visible_devices() {
@@ -935,6 +1107,44 @@ int gficf_cuda_last_timings(double* ms8) {
   return GFICF_OK;
 }
 
+int gficf_cuda_last_output(int32_t* out_mode, double* host_share, double* d2h_bytes) {
+  if (out_mode) *out_mode = tl_output.mode;
+  if (host_share) *host_share = tl_output.host_share;
+  if (d2h_bytes) *d2h_bytes = tl_timings[7];
+  return GFICF_OK;
+}
+
+int gficf_cuda_expand_host(const void* idx_colmajor, int32_t elem_bytes, int64_t n, int32_t k,
+                           const uint8_t* counts, int64_t row_lo, int64_t row_hi, double* out_colmajor,
+                           int32_t n_threads) {
+  if (!idx_colmajor || !counts || !out_colmajor || (elem_bytes != 8 && elem_bytes != 4) || n < 0 || k < 1 ||
+      k > 255 || row_lo < 0 || row_hi > n || row_hi < row_lo)
+    return GFICF_E_ARG;
+  double lut[256];
+  gficf_host::fill_weight_table(k, lut);
+  const gficf_host::ExpandJob job{idx_colmajor, elem_bytes, (long long)n, k, counts, (long long)row_lo,
+                                  out_colmajor, (long long)n * k, lut};
+  const long long rows = row_hi - row_lo;
+  const int nt = (int)std::max<long long>(1, std::min<long long>(n_threads > 0 ? n_threads : expand_threads(),
+                                                                 (rows + 4095) / 4096));
+  if (nt == 1) {
+    gficf_host::expand_rows(job, row_lo, row_hi);
+    return GFICF_OK;
+  }
+  std::atomic<long long> next(row_lo);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t)
+    pool.emplace_back([&] {
+      for (;;) {
+        const long long a = next.fetch_add(4096);
+        if (a >= row_hi) return;
+        gficf_host::expand_rows(job, a, std::min<long long>(row_hi, a + 4096));
+      }
+    });
+  for (auto& t : pool) t.join();
+  return GFICF_OK;
+}
+
 int gficf_cuda_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* variant) {
   if (grid) *grid = tl_launch.grid;
   if (block) *block = tl_launch.block;
@@ -977,9 +1187,11 @@ int jaccard_host_call(const void* idx, int elem, int64_t n, int32_t k, double* o
   g_active_devices.store(ndev);
   std::vector<SlabResult> res(ndev);
   std::vector<Slab> slabs;
+  const int out_mode = resolve_out_mode(out, (int)k, (int)mode);
   for (int r = 0; r < ndev; ++r) {
     slabs.emplace_back(r, ndev, idx, (long long)n, (int)k, rows_per, out, (int)mode);
     slabs.back().elem = elem;
+    slabs.back().out_mode = out_mode;
   }
   auto first_error = [&]() {
     for (auto& r : res)
@@ -1031,7 +1243,9 @@ int jaccard_host_call(const void* idx, int elem, int64_t n, int32_t k, double* o
     tm[3] = std::max<double>(tm[3], r.ms_d2h);
     tm[5] = std::max<double>(tm[5], r.ms_gather);
     tm[6] += r.launches;
+    tm[7] += r.d2h_bytes;
   }
+  tl_output = {res[0].out_mode, res[0].host_items};
   tm[4] = std::chrono::duration<double, std::milli>(t1 - t0).count();
   memcpy(tl_timings, tm, sizeof tm);
   if (flags & kFlagBadId)
@@ -1085,6 +1299,7 @@ int gficf_cuda_comm_init_rank(const void* id128, int32_t nranks, int32_t rank, i
   g_mp.nranks = nranks;
   g_mp.rank = rank;
   g_mp.dev = device;
+  g_sharers.store(nranks);  // one node: the ranks share the host's cores
   return GFICF_OK;
   API_END
 }
@@ -1113,6 +1328,7 @@ int gficf_cuda_jaccard_rank(const double* idx, int64_t n, int32_t k, double* out
   Slab s(g_mp.rank, nr, idx, (long long)n, (int)k, rows_per, out, GFICF_MODE_PARALLEL);
   s.dev = g_mp.dev;
   s.comm = g_mp.comm;
+  s.out_mode = resolve_out_mode(out, (int)k, GFICF_MODE_PARALLEL);
   SlabResult res;
   device_phase0(s, &res);
   DeviceWs& ws = g_ws[s.dev];
@@ -1156,8 +1372,9 @@ int gficf_cuda_jaccard_rank(const double* idx, int64_t n, int32_t k, double* out
   const auto t1 = std::chrono::steady_clock::now();
   double tm[8] = {res.ms_h2d, res.ms_k0, res.ms_k1, res.ms_d2h,
                   std::chrono::duration<double, std::milli>(t1 - t0).count(), res.ms_gather,
-                  (double)res.launches, 0};
+                  (double)res.launches, res.d2h_bytes};
   memcpy(tl_timings, tm, sizeof tm);
+  tl_output = {res.out_mode, res.host_items};
   return GFICF_OK;
   API_END
 }
@@ -1228,7 +1445,7 @@ int gficf_cuda_wait_dev(const uint32_t* d_flag, uint32_t expected, uint32_t* d_f
   size_t errlen = 0;
   API_BEGIN
   if (!d_flag || !d_flags) return GFICF_E_ARG;
-  wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_flag, expected, d_flags);
+  wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_flag, expected, d_flags, peer_spin_clocks(0));
   CU_TRY(cudaGetLastError());
   return GFICF_OK;
   API_END
@@ -1247,7 +1464,7 @@ int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_
   if (total <= 0) return GFICF_OK;
   expand_fixed_kernel<uint8_t><<<grid_1d(total, kExpandThreads, 8), kExpandThreads, 0, (cudaStream_t)stream>>>(
       d_idx_i32, k, row_stride(k), row_lo, row_hi, d_u, d_from, d_to, d_w, d_ready, n_ready, expected,
-      chunk_rows, d_flags);
+      chunk_rows, d_flags, peer_spin_clocks(0));
   CU_TRY(cudaGetLastError());
   return GFICF_OK;
   API_END
@@ -1305,6 +1522,49 @@ int gficf_cuda_jaccard_counts_dev(const int32_t* d_idx_i32, int64_t n, int32_t k
   if (!launch_fast<1>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u, d_flags,
                          (cudaStream_t)stream))
     return GFICF_E_LIMIT;
+  return GFICF_OK;
+  DEV_END
+}
+
+int gficf_cuda_jaccard_counts_tagged_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                                         int64_t row_hi, uint8_t* d_u, uint32_t tag, uint32_t* d_flags,
+                                         void* stream) {
+  DEV_BEGIN
+  if (!d_idx_i32 || !d_u || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
+  if ((tag & ~0x80u) || k > 127) return GFICF_E_LIMIT;
+  if (!launch_fast<1>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u, d_flags,
+                      (cudaStream_t)stream, tag))
+    return GFICF_E_LIMIT;
+  return GFICF_OK;
+  DEV_END
+}
+
+int gficf_cuda_expand_stream_dev(const int32_t* d_idx_i32, int32_t k, const int64_t* seg_lo,
+                                 const int64_t* seg_hi, int32_t n_seg, const uint8_t* d_u, double* d_from,
+                                 double* d_to, double* d_w, uint32_t tag, int64_t timeout_ms,
+                                 uint32_t* d_flags, void* stream) {
+  DEV_BEGIN
+  if (!d_idx_i32 || !d_u || !d_from || !d_to || !d_w || !d_flags || !seg_lo || !seg_hi) return GFICF_E_ARG;
+  if (k < 1 || k > 127 || (tag & ~0x80u) || n_seg < 0 || n_seg > kMaxStreamSegs) return GFICF_E_LIMIT;
+  StreamSegs segs;
+  int ns = 0;
+  long long longest = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (seg_lo[i] < 0 || seg_hi[i] < seg_lo[i]) return GFICF_E_ARG;
+    if (seg_hi[i] == seg_lo[i]) continue;
+    segs.lo[ns] = seg_lo[i];
+    segs.hi[ns] = seg_hi[i];
+    longest = std::max<long long>(longest, (seg_hi[i] - seg_lo[i]) * (long long)k);
+    ++ns;
+  }
+  if (!ns) return GFICF_OK;
+  // the resident CTAs (8 per SM) are shared evenly by the segments: every sub-grid then advances
+  // through its segment at the same rate as the ranks that produce the segments
+  long long gx = std::max<long long>(1, (long long)sm_count() * 8 / ns);
+  gx = std::min<long long>(gx, (longest + kExpandThreads - 1) / kExpandThreads);
+  expand_stream_kernel<<<dim3((unsigned)gx, (unsigned)ns), kExpandThreads, 0, (cudaStream_t)stream>>>(
+      d_idx_i32, k, row_stride(k), segs, d_u, d_from, d_to, d_w, tag, peer_spin_clocks(timeout_ms), d_flags);
+  CU_TRY(cudaGetLastError());
   return GFICF_OK;
   DEV_END
 }

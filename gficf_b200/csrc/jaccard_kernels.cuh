@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, GFICF_SMALL_MINB)
 jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, long long row_hi,
                        double* __restrict__ o_from, double* __restrict__ o_to,
                        double* __restrict__ o_w, uint8_t* __restrict__ o_u,
-                       unsigned* __restrict__ flags) {
+                       unsigned* __restrict__ flags, unsigned tag) {
   constexpr bool COUNTS_ONLY = OUT != 0;
   constexpr bool MUT = OUT == 2;
   using G = SmallK<KP>;
@@ -363,7 +363,7 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     if (valid) {
       const long long r = (row - row_lo) * (long long)k + lane;
       if (COUNTS_ONLY) {
-        o_u[r] = (uint8_t)u;
+        o_u[r] = (uint8_t)(u | tag);  // tag: the epoch bit of the streaming peer gather (else 0)
       } else {
         const bool nz = u > 0;  // :48 if(u>0), else the zero-filled row stays
         __stcs(o_from + r, nz ? (double)(row + 1) : 0.0);
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kWideWarps * 32, GFICF_WIDE_MINB)
 jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo,
                       long long row_hi, double* __restrict__ o_from, double* __restrict__ o_to,
                       double* __restrict__ o_w, uint8_t* __restrict__ o_u,
-                      unsigned* __restrict__ flags) {
+                      unsigned* __restrict__ flags, unsigned tag) {
   constexpr int TS = 1 << LOG_TS, SHIFT = 32 - LOG_TS;
   constexpr bool COUNTS_ONLY = OUT != 0;
   constexpr bool MUT = OUT == 2;  // needs k <= 127 (bit 7 of the count byte)
@@ -568,7 +568,7 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
       const int u = scnt[tid];
       const long long r = (row - row_lo) * (long long)k + tid;
       if (COUNTS_ONLY) {
-        o_u[r] = (uint8_t)u;
+        o_u[r] = (uint8_t)(u | tag);
       } else {
         const bool nz = u > 0;
         __stcs(o_from + r, nz ? (double)(row + 1) : 0.0);
@@ -727,7 +727,7 @@ jaccard_exact_kernel(const int* __restrict__ idx, int k, int kp, long long row_l
 // When `ready` is given, every CTA first waits until ready[0..n_ready) >= expected: the counts of
 // this row range are being stored into this GPU's memory by PEER GPUs' count kernels (NVLink
 // stores), and each peer raises its flag (signal_kernel) once its kernel has finished.  A bounded spin: after
-// ~2^31 clocks the kernel gives up and reports GFICF_FLAG_PEER_TIMEOUT instead of hanging the GPU.
+// spin_clocks the kernel gives up and reports GFICF_FLAG_PEER_TIMEOUT instead of hanging the GPU.
 constexpr unsigned kFlagPeerTimeout = 8u;
 
 constexpr int kExpandThreads = 256;
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(kExpandThreads)
 expand_fixed_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo, long long row_hi,
                     const CT* d_u, double* __restrict__ o_from, double* __restrict__ o_to,
                     double* __restrict__ o_w, const volatile unsigned* ready, int n_ready,
-                    unsigned expected, long long chunk_rows, unsigned* flags) {
+                    unsigned expected, long long chunk_rows, unsigned* flags, long long spin_clocks) {
   __shared__ double lut[256];
   const bool use_lut = k <= 255;
   if (use_lut && (int)threadIdx.x <= k) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
@@ -755,7 +755,7 @@ expand_fixed_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo
       // thread r waits for rank r's flag
       const long long t0 = clock64();
       while ((int)(ready[threadIdx.x] - (expected + chunk)) < 0) {
-        if (clock64() - t0 > (1ll << 31)) {
+        if (clock64() - t0 > spin_clocks) {
           atomicOr(flags, kFlagPeerTimeout);
           break;
         }
@@ -794,11 +794,81 @@ expand_fixed_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo
   }
 }
 
+// ---------------------------------------------------------------------------
+// Streaming expand of the peer-memory gather (host rank).  The count bytes of the rows in
+// segs[0..gridDim.y) are being stored into THIS GPU's memory by the count kernels of peer GPUs
+// (NVLink stores from their epilogues) while this kernel runs.  There are no flags and no fences:
+// every count byte carries the epoch's parity in bit 7 (`tag`, k <= 127), the buffer still holds the
+// other parity from the previous epoch, so a byte IS its own ready flag -- a thread polls its byte
+// (volatile load, served by L2, the point of coherence for stores arriving over NVLink) until the
+// parity matches.  blockIdx.y selects a segment (one per contributing rank); inside a segment the
+// sub-grid walks the rows linearly, like the peer's persistent count kernel does, so it trails the
+// producer by a fixed distance and normally never waits.
+// A bounded spin: after spin_clocks without progress the thread raises GFICF_FLAG_PEER_TIMEOUT and
+// leaves (the output is then invalid and the host side reports the error).
+// ---------------------------------------------------------------------------
+constexpr int kMaxStreamSegs = 16;
+struct StreamSegs {
+  long long lo[kMaxStreamSegs], hi[kMaxStreamSegs];
+};
+
+__device__ __forceinline__ unsigned ld_volatile_u8(const uint8_t* p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(kExpandThreads)
+expand_stream_kernel(const int* __restrict__ idx, int k, int kp, StreamSegs segs, const uint8_t* d_u,
+                     double* __restrict__ o_from, double* __restrict__ o_to, double* __restrict__ o_w,
+                     unsigned tag, long long spin_clocks, unsigned* flags) {
+  __shared__ double lut[128];
+  if ((int)threadIdx.x <= k && threadIdx.x < 128) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
+  __syncthreads();
+  const long long e_hi = segs.hi[blockIdx.y] * k;
+  const long long stride = (long long)gridDim.x * kExpandThreads;
+  const long long d_row = stride / k;
+  const int d_j = (int)(stride % k);
+  const long long g0 = segs.lo[blockIdx.y] * k + (long long)blockIdx.x * kExpandThreads + threadIdx.x;
+  long long row = g0 / k;  // absolute row: d_u, o_* are indexed by absolute edge number
+  int j = (int)(g0 % k);
+#pragma unroll 2
+  for (long long e = g0; e < e_hi; e += stride) {
+    const int t = __ldg(idx + row * (long long)kp + j);  // independent of the count byte: issued first
+    unsigned b = ld_volatile_u8(d_u + e);
+    if ((b & 0x80u) != tag) {
+      const long long t0 = clock64();
+      unsigned ns = 64;
+      do {
+        __nanosleep(ns);
+        if (ns < 2048) ns <<= 1;
+        b = ld_volatile_u8(d_u + e);
+        if ((b & 0x80u) != tag && clock64() - t0 > spin_clocks) {
+          atomicOr(flags, kFlagPeerTimeout);
+          return;
+        }
+      } while ((b & 0x80u) != tag);
+    }
+    const int u = (int)(b & 0x7Fu);
+    const bool nz = u > 0;
+    __stcs(o_from + e, nz ? (double)(row + 1) : 0.0);
+    __stcs(o_to + e, nz ? (double)(t + 1) : 0.0);
+    __stcs(o_w + e, lut[u]);
+    row += d_row;
+    j += d_j;
+    if (j >= k) {
+      j -= k;
+      ++row;
+    }
+  }
+}
+
 // holds the stream until *flag >= expected (bounded spin, see expand_fixed_kernel)
-__global__ void wait_kernel(const volatile unsigned* flag, unsigned expected, unsigned* flags) {
+__global__ void wait_kernel(const volatile unsigned* flag, unsigned expected, unsigned* flags,
+                            long long spin_clocks) {
   const long long t0 = clock64();
   while ((int)(*flag - expected) < 0) {
-    if (clock64() - t0 > (1ll << 31)) {
+    if (clock64() - t0 > spin_clocks) {
       atomicOr(flags, kFlagPeerTimeout);
       break;
     }

@@ -4,8 +4,25 @@
 // path needs: communicator setup for the GPUs of one process, all-gather of the
 // int32 index slabs, broadcast.
 #pragma once
+#include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <stddef.h>
+
+// The handful of NCCL declarations this file needs, restated from NCCL's public, ABI-stable C
+// interface (nccl.h of NCCL 2.x) so that building the library needs no NCCL headers: NCCL is a
+// RUN-time dependency of the multi-GPU calls only.  -DGFICF_USE_NCCL_HEADER takes them from <nccl.h>.
+#ifdef GFICF_USE_NCCL_HEADER
 #include <nccl.h>
+#else
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;  // every other value is an error; text from ncclGetErrorString
+typedef enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5,
+               ncclFloat16 = 6, ncclFloat32 = 7, ncclFloat64 = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3, ncclAvg = 4 } ncclRedOp_t;
+}
+#endif
 
 #include <string>
 

@@ -194,3 +194,29 @@ def expand_wait(idx_i32: torch.Tensor, k: int, row_lo: int, row_hi: int, counts_
                                                          sl[0].data_ptr(), sl[1].data_ptr(), sl[2].data_ptr(),
                                                          ready_ptr or None, n_ready, expected & 0xFFFFFFFF,
                                                          int(chunk_rows), flags.data_ptr(), _stream_ptr()))
+
+
+def jaccard_counts_tagged_to(idx_i32: torch.Tensor, n: int, k: int, row_lo: int, row_hi: int, out_ptr: int,
+                             tag: int, flags: torch.Tensor) -> None:
+    """Count kernel storing u | tag (tag = 0x00 / 0x80: the step parity of the streaming peer gather,
+    k <= 127) at the raw device address out_ptr (slab-relative; typically peer memory)."""
+    _require_cuda(idx_i32, torch.int32)
+    with torch.cuda.device(idx_i32.device):
+        _lib.check(_lib.lib().gficf_cuda_jaccard_counts_tagged_dev(idx_i32.data_ptr(), n, k, row_lo, row_hi, out_ptr,
+                                                                   tag, flags.data_ptr(), _stream_ptr()))
+
+
+def expand_stream(idx_i32: torch.Tensor, k: int, segments, counts_ptr: int, out3: torch.Tensor, tag: int,
+                  flags: torch.Tensor, timeout_ms: int = 0) -> None:
+    """Streaming expand on the host rank: the rows of `segments` [(lo, hi), ...] (absolute rows) are
+    expanded into out3[3, n*k] while peers are still storing the tagged counts at counts_ptr
+    (absolute edge order); every byte is polled until its parity bit equals `tag`."""
+    segs = [(int(a), int(b)) for a, b in segments if b > a]
+    if not segs:
+        return
+    lo = (C.c_int64 * len(segs))(*[a for a, _ in segs])
+    hi = (C.c_int64 * len(segs))(*[b for _, b in segs])
+    with torch.cuda.device(idx_i32.device):
+        _lib.check(_lib.lib().gficf_cuda_expand_stream_dev(idx_i32.data_ptr(), k, lo, hi, len(segs), counts_ptr,
+                                                           out3[0].data_ptr(), out3[1].data_ptr(), out3[2].data_ptr(),
+                                                           tag, int(timeout_ms), flags.data_ptr(), _stream_ptr()))

@@ -162,28 +162,48 @@ def rcpp_parallel_jaccard_coef_sharded(mat, n: int, k: int, out=None, group=None
 # are counted, so that the host rank's expansion of chunk c overlaps everybody's counting of
 # chunk c+1.
 # ---------------------------------------------------------------------------------------------
+def share_bounds(n: int, world: int, host_share: float, host_rank: int = 0):
+    """Contiguous row ranges in rank order: the host rank takes round(host_share * n) rows, the
+    other ranks equal parts of the rest (the last of them takes the remainder)."""
+    if world == 1:
+        return [(0, n)]
+    rows0 = int(round(min(1.0, max(0.0, host_share)) * n))
+    rest = n - rows0
+    per = (rest + world - 2) // (world - 1)
+    sizes, left = [], rest
+    for r in range(world):
+        if r == host_rank:
+            sizes.append(rows0)
+        else:
+            take = min(per, left)
+            sizes.append(take)
+            left -= take
+    assert left == 0
+    out, lo = [], 0
+    for take in sizes:
+        out.append((lo, lo + take))
+        lo += take
+    assert lo == n
+    return out
+
+
 def weighted_bounds(n: int, world: int, rho: float, host_rank: int = 0):
     """Row ranges per rank.  rho = (time to expand a row) / (time to count a row) on one GPU.
     Balancing  x*Tc + Te = (1-x)*Tc/(world-1)  gives the host rank's share x = (1 - rho*(world-1))/world."""
     if world == 1:
         return [(0, n)]
-    x = max(0.0, (1.0 - rho * (world - 1)) / world)
-    rows0 = int(round(x * n))
-    rest = n - rows0
-    per = (rest + world - 2) // (world - 1)
-    out, lo = [], 0
-    others = 0
-    for r in range(world):
-        if r == host_rank:
-            out.append((lo, lo + rows0))
-            lo += rows0
-        else:
-            hi = min(n, lo + per) if others < world - 2 else n
-            out.append((lo, hi))
-            lo = hi
-            others += 1
-    assert lo == n
-    return out
+    return share_bounds(n, world, max(0.0, (1.0 - rho * (world - 1)) / world), host_rank)
+
+
+def balanced_host_share(world: int, t_fused: float, t_count: float, t_expand: float) -> float:
+    """Host rank's share x of the rows for the streaming peer gather.  Per row: t_fused = fused
+    kernel (the host rank's own rows), t_count = count kernel (the peers' rows), t_expand = expand
+    kernel (the host rank expands every peer row).  Host: x*t_fused + (1-x)*t_expand; a peer:
+    (1-x)*t_count/(world-1); equal when x = (p - t_expand) / (t_fused + p - t_expand), p = t_count/(world-1)."""
+    if world <= 1:
+        return 1.0
+    p = t_count / (world - 1)
+    return min(1.0, max(0.0, (p - t_expand) / (t_fused + p - t_expand)))
 
 
 def chunk_bounds(lo: int, hi: int, chunks: int):
@@ -261,48 +281,49 @@ class PipelinedGather:
                     self.expand(idx_full, k, counts_all[lo * k:hi * k], lo, hi, out3)
 
 
-def chunk_major_bounds(n: int, world: int, rho: float, chunks: int, host_rank: int = 0):
-    """Row ranges [chunk][rank]: the matrix is cut into `chunks` contiguous pieces; inside each
-    piece the host rank takes the weighted share x (see weighted_bounds) and the other ranks equal
-    parts of the rest.  A chunk is therefore ONE contiguous row range for the host rank's expand."""
-    out = []
-    for c_lo, c_hi in chunk_bounds(0, n, chunks):
-        b = weighted_bounds(c_hi - c_lo, world, rho, host_rank)
-        out.append([(c_lo + lo, c_lo + hi) for lo, hi in b])
-    return out
-
-
 class PeerGather:
-    """Counts on every rank, gather FUSED into the count kernel, expansion on the host rank.
+    """Counts on every rank, gather FUSED into the count kernel, streaming expansion on the host rank.
 
     The host rank exports its count buffer (CUDA IPC); the other ranks map it and their count
-    kernels store the 1-byte results straight into the host rank's HBM over NVLink.  A flag per
-    rank (raised by a one-thread kernel behind each chunk) tells the host rank's expand kernel that
-    a chunk has landed; the expand of chunk c (one launch over the chunk's contiguous rows, waiting
-    for every rank's flag) overlaps everybody's counting of chunk c+1.  No collective kernel
-    competes for SMs with the persistent count kernels.
+    kernels store the 1-byte results straight into the host rank's HBM over NVLink -- ONE persistent
+    count launch per rank and step.  Every count byte carries the step's parity in bit 7 (k <= 127),
+    so a byte is its own ready flag: the host rank's expand kernel (one launch, one sub-grid per
+    contributing rank, each walking its rank's rows linearly like the count kernel that produces
+    them) polls the bytes it is about to expand and otherwise never synchronises -- no flags, no
+    fences, no per-chunk launches, no collective kernel competing for SMs.  The host rank computes
+    its own (smaller) row share with the fused kernel straight into the output before it expands.
+    The only other synchronisation is one ack flag per step: a peer may overwrite the buffer for
+    step s+1 only after the host rank's expand of step s has finished.
 
-    torch.distributed only carries the 64-byte IPC handle at construction."""
+    torch.distributed only carries the 64-byte IPC handle at construction and the flag bits in
+    finish()."""
 
-    def __init__(self, n: int, k: int, group=None, rho: float = 0.2, chunks: int = 4, host_rank: int = 0):
+    def __init__(self, n: int, k: int, group=None, host_share: float | None = None, host_rank: int = 0,
+                 timeout_ms: int = 0, rho: float | None = None, chunks: int | None = None):
         from . import device as D
 
+        if k > 127:
+            raise ValueError("the streaming peer gather carries the step parity in bit 7 of the count byte: k <= 127")
         self.D = D
         self.n, self.k, self.group, self.host = n, k, group, host_rank
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.plan = chunk_major_bounds(n, self.world, rho, chunks, host_rank)
-        self.nchunks = len(self.plan)
-        self.chunk_rows = self.plan[0][-1][1] - self.plan[0][0][0]  # rows per chunk (the last may be shorter)
+        if host_share is None:
+            # rho (legacy argument): expand / count cost ratio -> the same balance with t_fused = t_count
+            host_share = balanced_host_share(self.world, 1.0, 1.0 if rho is not None else 0.85,
+                                             rho if rho is not None else 0.2)
+        self.host_share = host_share
+        self.bounds = share_bounds(n, self.world, host_share, host_rank)
+        self.timeout_ms = timeout_ms
         self.epoch = 0
         self.launches = 0
         e = n * k
-        self.flag_off = (e + 255) // 256 * 256          # [world] chunk flags, then the ack flag
-        nbytes = self.flag_off + 4 * (self.world + 1)
+        self.flag_off = (e + 255) // 256 * 256          # the ack flag lives behind the counts
+        nbytes = self.flag_off + 256
         box = [None]
         ok, self.base = 1, 0
         if self.rank == host_rank:
             try:
-                self.base, handle = D.ipc_alloc(nbytes)
+                self.base, handle = D.ipc_alloc(nbytes)   # zero-filled: parity 0, the first step uses 0x80
                 box = [handle]
             except Exception:
                 ok = 0
@@ -325,10 +346,7 @@ class PeerGather:
             raise RuntimeError("peer-memory gather unavailable: the count buffer could not be mapped on every rank")
 
     def rows_of(self, rank: int) -> int:
-        return sum(p[rank][1] - p[rank][0] for p in self.plan)
-
-    def _flag(self, r):
-        return self.base + self.flag_off + 4 * r
+        return self.bounds[rank][1] - self.bounds[rank][0]
 
     def close(self):
         torch.cuda.synchronize()
@@ -339,29 +357,44 @@ class PeerGather:
             self.D.ipc_close(self.base)
 
     def step(self, idx_full, out3):
+        """One pass: asynchronous on the current stream.  out3: float64 [3, n*k] on the host rank."""
         D, k, n = self.D, self.k, self.n
-        base_val = self.epoch * self.nchunks
-        ack = self._flag(self.world)
-        if self.rank != self.host:
-            # the host rank must have consumed the previous step's counts before they are overwritten
-            D.wait_flag(ack, self.epoch, self.flags)
-        # every rank: its part of chunk c, then a flag raise in the host rank's memory; the host rank
-        # follows each of its own parts with the expand launch of that chunk (which waits for every
-        # rank's flag), so expanding chunk c overlaps everybody's counting of chunk c+1.
-        # (One single expand launch streaming behind the chunks -- expand_wait(chunk_rows=...) -- was
-        # measured slower: 1.46 vs 1.19 ms at 4 ranks, 2.30 vs 2.04 ms at 2.)
-        for c, ranges in enumerate(self.plan):
-            lo, hi = ranges[self.rank]
-            if hi > lo:
-                D.jaccard_counts_to(idx_full, n, k, lo, hi, self.base + lo * k, self.flags)
-                self.launches += 1
-            D.signal(self._flag(self.rank), base_val + c + 1)
-            if self.rank == self.host:
-                c_lo, c_hi = ranges[0][0], ranges[-1][1]
-                if c_hi > c_lo:
-                    D.expand_wait(idx_full, k, c_lo, c_hi, self.base + c_lo * k, out3, self._flag(0), self.world,
-                                  base_val + c + 1, self.flags)
-                    self.launches += 1
         self.epoch += 1
-        if self.rank == self.host:
-            D.signal(ack, self.epoch)
+        tag = (self.epoch & 1) << 7
+        ack = self.base + self.flag_off
+        lo, hi = self.bounds[self.rank]
+        if self.rank != self.host:
+            # the host rank must have expanded the previous step's counts before they are overwritten
+            D.wait_flag(ack, self.epoch - 1, self.flags)
+            if hi > lo:
+                D.jaccard_counts_tagged_to(idx_full, n, k, lo, hi, self.base + lo * k, tag, self.flags)
+                self.launches += 1
+            return
+        if hi > lo:  # own rows: fused kernel straight into the output, while the peers count
+            D.jaccard_edges(idx_full, n, k, lo, hi, out=out3[:, lo * k:hi * k], flags=self.flags)
+            self.launches += 1
+        segs = [b for r, b in enumerate(self.bounds) if r != self.host and b[1] > b[0]]
+        if segs:
+            D.expand_stream(idx_full, k, segs, self.base, out3, tag, self.flags, self.timeout_ms)
+            self.launches += 1
+        D.signal(ack, self.epoch)
+
+    def finish(self, idx_full, out3) -> int:
+        """Collective, after the last step(): agrees on the flag bits of all ranks.  A peer timeout
+        raises on every rank (the output is invalid); rows with repeated ids (DUP_ID / HASH_FAIL on
+        any rank invalidate fast counts everywhere) are recomputed by the host rank with the exact
+        multiset kernel + expand.  Returns the OR of the flags."""
+        D = self.D
+        torch.cuda.current_stream().synchronize()
+        bits = torch.stack([(self.flags[0] >> b) & 1 for b in range(4)])
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=self.group)
+        allf = int(bits[0]) | (int(bits[1]) << 1) | (int(bits[2]) << 2) | (int(bits[3]) << 3)
+        if allf & 8:
+            raise RuntimeError("peer-memory gather timed out (GFICF_FLAG_PEER_TIMEOUT): a rank did not deliver its "
+                               "counts / its ack within the spin bound; the output is invalid")
+        if allf & (D.FLAG_DUP_ID | D.FLAG_HASH_FAIL) and self.rank == self.host:
+            counts = D.jaccard_counts_exact(idx_full, self.n, self.k, False)
+            D.expand(idx_full, self.k, counts, mode=0, row_lo=0, row_hi=self.n, out=out3)
+            torch.cuda.current_stream().synchronize()
+        self.flags.zero_()
+        return allf

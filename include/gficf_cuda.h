@@ -112,9 +112,30 @@ int gficf_cuda_release(void);
 
 /* Timings (milliseconds, CUDA events) of the last gficf_cuda_jaccard call on
  * this thread: [0] H2D, [1] layout pre-pass, [2] Jaccard kernel(s),
- * [3] D2H (overlapped portion included), [4] whole call wall-clock,
- * [5] index all-gather (n_devices>1), [6] kernels launched, [7] reserved. */
+ * [3] D2H / output phase (overlapped portion included), [4] whole call wall-clock,
+ * [5] index all-gather (n_devices>1), [6] kernels launched, [7] bytes copied device -> host. */
 int gficf_cuda_last_timings(double* ms8);
+
+/* How the last gficf_cuda_jaccard / _i32 / _rank call on this thread produced its output columns:
+ * *out_mode 1 = dma (the device wrote 24 B/edge, the copy engine moved them), 2 = host (only the
+ * 1-byte intersection counts crossed PCIe; host threads wrote from = i+1, to = idx(i,j),
+ * weight = table[u] straight into the caller's matrix, bit-identical by construction), 3 = hybrid
+ * (both at once, (column, row-chunk) pieces claimed dynamically); *host_share = share of the pieces
+ * written by host threads; *d2h_bytes = bytes that crossed PCIe towards the host.  The mode is chosen
+ * per call: hybrid for page-locked output, host for pageable output (what R passes), dma for k > 255
+ * or the serial export; GFICF_CUDA_OUT_MODE=dma|host|hybrid overrides, GFICF_CUDA_EXPAND_THREADS
+ * sets the number of host threads. */
+int gficf_cuda_last_output(int32_t* out_mode, double* host_share, double* d2h_bytes);
+
+/* The host half of the counts-over-PCIe output on its own: rows [row_lo,row_hi) of the fixed-slot
+ * export written into out_colmajor ((n*k) x 3) from the caller's matrix (elem_bytes 8 = double,
+ * 4 = int32; column-major, 1-based) and the rows' intersection counts as the device kernels produce
+ * them (gficf_cuda_jaccard_counts_dev, k <= 255; counts[(i-row_lo)*k + j]).  Pure host code, no
+ * device needed: for hosts that collect the 1-byte counts themselves (several nodes, a job queue).
+ * Replaces the stores rcpp_parallel_jaccard_coeff.cpp:48-52.  n_threads <= 0: automatic. */
+int gficf_cuda_expand_host(const void* idx_colmajor, int32_t elem_bytes, int64_t n, int32_t k,
+                           const uint8_t* counts, int64_t row_lo, int64_t row_hi, double* out_colmajor,
+                           int32_t n_threads);
 
 /* ======================================================================== *
  *  One process per GPU (MPI-style hosts, torchrun): every rank calls the same
@@ -161,6 +182,26 @@ int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_
                                const uint8_t* d_u, double* d_from, double* d_to, double* d_w,
                                const uint32_t* d_ready, int32_t n_ready, uint32_t expected,
                                int64_t chunk_rows, uint32_t* d_flags, void* stream);
+
+/* Streaming form of the peer-memory gather (no flags, no fences, one launch per rank and step; the
+ * default of gficf_b200.sharding.PeerGather).  Every count byte carries the step's parity in bit 7
+ * (`tag` = 0x00 / 0x80, alternating from step to step; k <= 127), so a byte is its own ready flag:
+ *   gficf_cuda_jaccard_counts_tagged_dev   the count kernel of gficf_cuda_jaccard_counts_dev, storing
+ *                                          u | tag (d_u: typically the host rank's mapped buffer)
+ *   gficf_cuda_expand_stream_dev           host rank: expands the rows of n_seg row segments (one per
+ *                                          contributing rank; seg_lo/seg_hi are HOST arrays of absolute
+ *                                          rows) while the peers are still storing into d_u, polling each
+ *                                          byte until its parity equals `tag`.  d_u, d_from, d_to, d_w are
+ *                                          indexed by ABSOLUTE edge number i*k+j.  timeout_ms bounds
+ *                                          every spin (0: GFICF_CUDA_PEER_TIMEOUT_MS, default 20000);
+ *                                          GFICF_FLAG_PEER_TIMEOUT in *d_flags means the output is invalid. */
+int gficf_cuda_jaccard_counts_tagged_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
+                                         int64_t row_hi, uint8_t* d_u, uint32_t tag, uint32_t* d_flags,
+                                         void* stream);
+int gficf_cuda_expand_stream_dev(const int32_t* d_idx_i32, int32_t k, const int64_t* seg_lo,
+                                 const int64_t* seg_hi, int32_t n_seg, const uint8_t* d_u, double* d_from,
+                                 double* d_to, double* d_w, uint32_t tag, int64_t timeout_ms,
+                                 uint32_t* d_flags, void* stream);
 
 /* ======================================================================== *
  *  Device-buffer entry points (resident data: the benchmarked kernels, and

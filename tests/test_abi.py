@@ -74,3 +74,39 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "libgficf_oracle" not in text and "libgficf_ref" not in text, f
+
+
+def test_host_expand_writes_the_reference_rows(oracle):
+    """The host half of the counts-over-PCIe output mode (gficf_cuda_expand_host, csrc/host_expand.cpp)
+    needs no device: given the reference's own intersection counts it must write the reference's
+    bytes -- all three columns, f64 and int32 input, partial tiles, u == 0 rows, every k <= 255."""
+    import ctypes as C
+
+    import gficf_b200
+    from tests.conftest import random_knn
+
+    L = gficf_b200.lib()
+    rng = np.random.default_rng(21)
+    for n, k, distinct in ((5000, 30, True), (700, 15, False), (333, 100, True), (300, 255, True), (64, 1, True),
+                           (4099, 7, True)):
+        r = random_knn(rng, n, k, distinct=distinct, with_self=not distinct)
+        want = oracle.parallel(r)
+        lut = np.array([u / (2.0 * k - u) for u in range(k + 1)])
+        u = np.searchsorted(lut, want[:, 2]).astype(np.uint8)  # the reference's counts, from its weights
+        assert np.array_equal(lut[u], want[:, 2])
+        for as_int in (False, True):
+            src = np.asfortranarray(r.astype(np.int32)) if as_int else r
+            for threads in (1, 3):
+                out = np.full((n * k, 3), -3.0, dtype=np.float64, order="F")
+                rc = L.gficf_cuda_expand_host(src.ctypes.data, 4 if as_int else 8, n, k, u.ctypes.data, 0, n,
+                                              out.ctypes.data, threads)
+                assert rc == 0 and np.array_equal(out, want), (n, k, as_int, threads)
+        # a row range in the middle: only those rows are written, counts are slab-relative
+        lo, hi = n // 3, n // 3 + max(1, n // 5)
+        out = np.full((n * k, 3), -3.0, dtype=np.float64, order="F")
+        sub = np.ascontiguousarray(u[lo * k:hi * k])
+        assert L.gficf_cuda_expand_host(r.ctypes.data, 8, n, k, sub.ctypes.data, lo, hi, out.ctypes.data, 2) == 0
+        assert np.array_equal(out[lo * k:hi * k], want[lo * k:hi * k])
+        assert (out[:lo * k] == -3.0).all() and (out[hi * k:] == -3.0).all()
+    bad = np.zeros(4)
+    assert L.gficf_cuda_expand_host(bad.ctypes.data, 2, 2, 2, bad.ctypes.data, 0, 2, bad.ctypes.data, 1) == 1

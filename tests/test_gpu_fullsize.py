@@ -58,11 +58,10 @@ def test_k30_full_sizes_device_path(cuda, oracle, n, k, scramble):
     out, flags = D.jaccard_edges(padded, n, k, flags=flags)
     torch.cuda.synchronize()
     assert int(flags[0]) == 0
-    r = None
-    rows = ()
-    if n <= 1_000_000:
-        r = synth.to_r_matrix(idx0)
-        rows = [(0, 300), (n // 2, n // 2 + 300), (n - 300, n)]
+    # the oracle itself on head / middle / tail rows, at 4M too (the rows gather from the whole matrix)
+    r = synth.to_r_matrix(idx0)
+    m = 300 if n <= 1_000_000 else 700
+    rows = [(0, m), (n // 2, n // 2 + m), (n - m, n)]
     _check_properties(out, idx0, k, oracle, r, rows)
 
 

@@ -91,17 +91,51 @@ for n, k, rho in ((300_000, 30, 0.19), (50_001, 15, 0.6), (20_000, 100, 0.0), (7
         assert torch.equal(out3, ref), (n, k)
         assert int(pg.flags[0]) == 0
     dist.barrier()
-    # the same schedule with the gather fused into the count kernel (peer stores over NVLink)
-    peer = sharding.PeerGather(n, k, rho=rho, chunks=4)
-    if rank == 0:
-        out3.fill_(-1.0)
-    for it in range(3):
-        peer.step(padded, out3)
-    torch.cuda.synchronize()
-    if rank == 0:
-        assert torch.equal(out3, ref), ("peer", n, k)
-    assert int(peer.flags[0]) == 0
-    peer.close()
+    # the gather fused into the count kernel (parity-tagged peer stores over NVLink), streaming expand
+    for share, host in ((None, 0), (0.0, 0), (0.37, 0), (0.2, dist.get_world_size() - 1)):
+        peer = sharding.PeerGather(n, k, host_share=share, host_rank=host, timeout_ms=5000)
+        o3 = torch.full((3, n * k), -1.0, dtype=torch.float64, device="cuda") if rank == host else None
+        for it in range(3):  # odd and even epochs on the same buffer
+            peer.step(padded, o3)
+        assert peer.finish(padded, o3) == 0
+        if rank == host:
+            ref1, _ = D.jaccard_edges(padded, n, k)
+            assert torch.equal(o3, ref1), ("peer", n, k, share, host)
+        peer.close()
+# streaming peer gather: a repeated id anywhere -> finish() reruns the exact path on the host rank
+n, k = 40_000, 30
+idx0 = synth.knn_index(n, k, scramble=True, device="cuda")
+idx0[n - 3, 0] = idx0[n - 3, k - 1]
+padded, fl = D.pad_rows(idx0)
+peer = sharding.PeerGather(n, k, timeout_ms=5000)
+o3 = torch.full((3, n * k), -1.0, dtype=torch.float64, device="cuda") if rank == 0 else None
+peer.step(padded, o3)
+assert peer.finish(padded, o3) & (D.FLAG_DUP_ID | D.FLAG_HASH_FAIL)
+if rank == 0:
+    assert np.array_equal(o3.cpu().numpy().T, Oracle().parallel(synth.to_r_matrix(idx0)))
+peer.close()
+# configs[4]'s shape (k = 100) at 1M cells over all ranks: whole matrix against the single-GPU fused
+# kernel, and the oracle on head / middle / tail rows
+n, k = 1_000_000, 100
+idx0 = synth.knn_index(n, k, scramble=True, device="cuda")
+padded, fl = D.pad_rows(idx0)
+peer = sharding.PeerGather(n, k, timeout_ms=5000)
+o3 = torch.empty((3, n * k), dtype=torch.float64, device="cuda") if rank == 0 else None
+for it in range(2):
+    peer.step(padded, o3)
+assert peer.finish(padded, o3) == 0
+if rank == 0:
+    ref1, _ = D.jaccard_edges(padded, n, k)
+    assert torch.equal(o3, ref1), "k=100 1M cells"
+    del ref1
+    r = synth.to_r_matrix(idx0)
+    orc = Oracle()
+    for lo, hi in ((0, 300), (n // 2, n // 2 + 300), (n - 300, n)):
+        assert np.array_equal(o3[:, lo * k:hi * k].cpu().numpy().T, orc.parallel_rows(r, lo, hi)), (lo, hi)
+    del r
+peer.close()
+del o3, padded, idx0
+torch.cuda.empty_cache()
 # the library's own one-rank-per-GPU entry on shared page-locked host matrices
 from gficf_b200 import multiproc
 multiproc.comm_init_from_torch()
@@ -146,9 +180,9 @@ def test_one_process_per_gpu_nccl(cuda, tmp_path):
         pytest.skip("needs >= 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(_WORKER % {"root": ROOT})
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(nd, 4)),
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(nd, 8)),
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
-                         capture_output=True, text=True, timeout=900)
+                         capture_output=True, text=True, timeout=1500)
     log = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(log):
         with open(os.path.join(log, "worker_multi.log"), "w") as f:

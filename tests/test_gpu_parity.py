@@ -64,7 +64,7 @@ def test_large_k_device_counts(cuda, oracle):
     assert torch.equal(fused, out)
 
 
-def test_exact_kernel_beyond_fast_range_is_reachable(cuda):
+def test_exact_kernel_beyond_fast_range_is_reachable(cuda, oracle):
     """k > 1024 has no fast kernel: the device entry says so, the host entry uses the exact path."""
     from gficf_b200 import device as D
 
@@ -74,6 +74,56 @@ def test_exact_kernel_beyond_fast_range_is_reachable(cuda):
     with pytest.raises(cuda.GficfCudaError) as e:
         D.jaccard_counts(padded, n, k)
     assert e.value.code == 5
+    # the host ABI (what R calls) at k = 1030: exact kernel + expand, both exports
+    r = synth.to_r_matrix(idx0)
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(r), oracle.parallel(r))
+    assert np.array_equal(cuda.jaccard_coeff(r), oracle.serial(r))
+
+
+@pytest.mark.parametrize("mode", ["dma", "host", "hybrid", None])
+def test_output_modes_of_the_host_abi(cuda, oracle, mode, monkeypatch):
+    """The three ways the (n*k) x 3 doubles reach the caller's matrix (include/gficf_cuda.h,
+    gficf_cuda_last_output) give the reference's bytes: device-written columns moved by the copy
+    engine, host threads writing the columns from the 1-byte device counts, and both at once --
+    on page-locked and on pageable buffers, for f64 and int32 input, incl. u == 0 rows, a repeated
+    id (exact path) and sizes that leave partial pieces."""
+    if mode is None:
+        monkeypatch.delenv("GFICF_CUDA_OUT_MODE", raising=False)
+    else:
+        monkeypatch.setenv("GFICF_CUDA_OUT_MODE", mode)
+    rng = np.random.default_rng(12)
+    cases = [(synth.to_r_matrix(synth.knn_index(200_003, 30, scramble=True)), "planted"),
+             (synth.to_r_matrix(synth.knn_index(60_001, 15, family="uniform")), "uniform: u == 0 almost everywhere"),
+             (random_knn(rng, 3001, 100), "k=100"), (random_knn(rng, 700, 200), "k=200"),
+             (random_knn(rng, 37, 3, with_self=True), "tiny")]
+    for r, what in cases:
+        n, k = r.shape
+        want = oracle.parallel(r)
+        for pinned in (False, True):
+            for as_int in (False, True):
+                src = r.astype(np.int32) if as_int else r
+                if pinned:
+                    buf = cuda.pinned_empty((n, k), dtype=src.dtype)
+                    buf[...] = src
+                    src = buf
+                    out = cuda.pinned_empty((n * k, 3))
+                else:
+                    src = np.asfortranarray(src)
+                    out = np.empty((n * k, 3), dtype=np.float64, order="F")
+                out[...] = -7.0
+                got = cuda.rcpp_parallel_jaccard_coef(src, False, 1, out=out)
+                assert np.array_equal(np.asarray(got), want), (what, mode, pinned, as_int)
+                om = cuda.last_output()
+                if mode == "dma":
+                    assert om["mode"] == "dma" and om["d2h_bytes"] == 24 * n * k
+                elif mode == "host" or (mode is None and not pinned):
+                    assert om["mode"] == "host" and om["host_share"] == 1.0 and om["d2h_bytes"] == n * k
+                elif pinned:
+                    assert om["mode"] == "hybrid" and n * k <= om["d2h_bytes"] <= 25 * n * k
+    # a repeated id: the fast counts are discarded, the exact path rewrites everything
+    r2 = random_knn(rng, 5000, 30)
+    r2[77, 3] = r2[77, 9]
+    assert np.array_equal(cuda.rcpp_parallel_jaccard_coef(r2), oracle.parallel(r2))
 
 
 @pytest.mark.parametrize("n,k", [(500, 8), (300, 30), (200, 64), (150, 100), (260, 200)])

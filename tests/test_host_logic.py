@@ -42,14 +42,54 @@ def test_error_codes_are_named():
     assert "GFICF_E_RANGE" in str(e) and e.code == 2 and e.message == "bad id"
 
 
-def test_chunk_major_plan_covers_every_row_once():
+def test_share_bounds_cover_every_row_once_for_any_host_rank():
     for n in (7, 1000, 4_000_000):
-        for world in (2, 4, 8):
-            for rho in (0.0, 0.29, 1.0):
-                plan = sharding.chunk_major_bounds(n, world, rho, 4)
-                flat = [r for chunk in plan for r in chunk]
-                assert flat[0][0] == 0 and flat[-1][1] == n
-                assert all(a[1] == b[0] for a, b in zip(flat, flat[1:]))
-                # a chunk is one contiguous range for the host rank's expand kernel
-                for chunk in plan:
-                    assert chunk[0][0] <= chunk[-1][1] and all(lo <= hi for lo, hi in chunk)
+        for world in (2, 3, 4, 8):
+            for share in (0.0, 0.075, 0.39, 1.0):
+                for host in (0, 1, world - 1):
+                    b = sharding.share_bounds(n, world, share, host)
+                    assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+                    assert all(x[1] == y[0] for x, y in zip(b, b[1:])) and all(hi >= lo for lo, hi in b)
+                    assert b[host][1] - b[host][0] == int(round(share * n))
+                    rest = [hi - lo for r, (lo, hi) in enumerate(b) if r != host]
+                    assert max(rest) - min(rest) <= world  # the peers' parts are even (up to the remainder)
+
+
+def test_weighted_bounds_with_the_host_on_the_last_rank():
+    # r01 defect: the last non-host rank was stretched to n before the host's range was appended
+    assert sharding.weighted_bounds(1000, 4, 0.1, 3) == [(0, 275), (275, 550), (550, 825), (825, 1000)]
+    for host in range(4):
+        b = sharding.weighted_bounds(1001, 4, 0.1, host)
+        assert b[0][0] == 0 and b[-1][1] == 1001 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+
+
+def test_balanced_host_share_equalises_host_and_peer_time():
+    tf, tc, te = 3.04, 2.6, 0.62  # ms per 4M rows: fused, count, expand (B200, k=30)
+    for world in (2, 4):
+        x = sharding.balanced_host_share(world, tf, tc, te)
+        host = x * tf + (1 - x) * te
+        peer = (1 - x) * tc / (world - 1)
+        assert 0 < x < 1 and abs(host - peer) < 1e-9
+    # from ~6 ranks on the host rank only expands
+    assert sharding.balanced_host_share(8, tf, tc, te) == 0.0
+    assert sharding.balanced_host_share(1, tf, tc, te) == 1.0
+
+
+def test_parity_tag_protocol_model():
+    """Model of the streaming peer gather's data-as-flag protocol (expand_stream_kernel): a consumer
+    that only accepts a byte whose bit 7 equals the epoch's parity never reads a stale count, whatever
+    order the producers' byte stores land in, over several epochs on the same buffer."""
+    rng = np.random.default_rng(5)
+    e, k = 4096, 100
+    buf = np.zeros(e, dtype=np.uint8)            # zero-filled: parity 0, the first epoch uses 0x80
+    for epoch in range(1, 6):
+        tag = (epoch & 1) << 7
+        truth = rng.integers(0, k + 1, e).astype(np.uint8)
+        order = rng.permutation(e)
+        done = np.zeros(e, dtype=bool)
+        for piece in np.array_split(order, 7):   # stores land in arbitrary pieces
+            ready = (buf & 0x80) == tag          # what the consumer would accept right now
+            assert not (ready & ~done).any()     # never a byte that this epoch has not written yet
+            buf[piece] = truth[piece] | tag
+            done[piece] = True
+        assert ((buf & 0x80) == tag).all() and np.array_equal(buf & 0x7F, truth)

@@ -42,3 +42,35 @@ def test_rpkg_bodies_match_reference(cuda, oracle):
     with pytest.raises(RuntimeError) as e:
         h.call(0, bad)
     assert "(2)" in str(e.value)
+
+
+def test_makevars_recipe_builds(tmp_path):
+    """The build recipe a gficf maintainer gets (gficf_b200/rpkg/src/Makevars.cuda, INTEGRATION.md
+    section 1), run as written: tools/stage_rpkg.sh lays the files out as src/ + src/cuda/ of the R
+    package, then `make` follows Makevars' own nvcc rule and link line, with the few rules R's
+    shlib.mk supplies (compile *.cpp with PKG_CPPFLAGS, link $(SHLIB) with PKG_LIBS) restated here
+    and the stand-in R runtime on the include path (R itself is not installed)."""
+    import ctypes
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = tmp_path / "gficf"
+    subprocess.run([os.path.join(root, "tools", "stage_rpkg.sh"), str(pkg)], check=True, capture_output=True)
+    src = pkg / "src"
+    staged = sorted(os.listdir(src / "cuda"))
+    assert "gficf_cuda.cu" in staged and "snn_kernels.cuh" in staged and "gficf_cuda.h" in staged
+    (src / "rshlib.mk").write_text(
+        "include Makevars\n"
+        "OBJS = rcpp_parallel_jaccard_coeff.o jaccard_coeff.o gficf_cuda_devices.o\n"
+        "%.o: %.cpp\n\tg++ -std=c++11 -fPIC -O2 -I$(RSHIM) $(PKG_CPPFLAGS) -c $< -o $@\n"
+        "$(SHLIB): $(OBJS)\n\tg++ -shared -o $@ $(OBJS) $(PKG_LIBS)\n")
+    r = subprocess.run(["make", "-f", "rshlib.mk", "SHLIB=gficf.so", "RSHIM=" + os.path.join(root, "oracle", "rshim"),
+                        "gficf.so"], cwd=src, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "-gencode arch=compute_100a,code=sm_100a" in r.stdout
+    so = ctypes.CDLL(str(src / "gficf.so"))
+    assert so.gficf_cuda_device_count() >= 0          # the C ABI is inside the package's shared object
+    assert b"sm_100a" in ctypes.cast(so.gficf_cuda_version, ctypes.CFUNCTYPE(ctypes.c_char_p))()
+    sym = subprocess.run(["nm", "-D", "--defined-only", str(src / "gficf.so")], capture_output=True, text=True).stdout
+    assert "rcpp_parallel_jaccard_coef" in sym and "jaccard_coeff" in sym

@@ -81,7 +81,7 @@ def test_slab_bounds_cover_rows_exactly():
             assert all(hi - lo <= sharding.slab_rows(n, world) for lo, hi in spans)
 
 
-def _pipe_worker(rank, world, port, n, k, rho, q):
+def _pipe_worker(rank, world, port, n, k, rho, host, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -105,24 +105,24 @@ def _pipe_worker(rank, world, port, n, k, rho, q):
             out3[1, lo * k_:hi * k_] = torch.from_numpy(np.where(nz, idx_[lo:hi].numpy().reshape(-1) + 1.0, 0.0))
             out3[2, lo * k_:hi * k_] = torch.from_numpy(lut[u])
 
-        pg = sharding.PipelinedGather(n, k, rho=rho, chunks=3, compute_counts=compute, expand=expand)
+        pg = sharding.PipelinedGather(n, k, rho=rho, chunks=3, host_rank=host, compute_counts=compute, expand=expand)
         counts = torch.zeros(n * k, dtype=torch.uint8)
-        out3 = torch.full((3, n * k), -1.0, dtype=torch.float64) if rank == 0 else None
+        out3 = torch.full((3, n * k), -1.0, dtype=torch.float64) if rank == host else None
         pg.step(idx, counts, out3)
         pg.step(idx, counts, out3)  # the schedule is re-entrant
-        q.put((rank, pg.bounds, out3.numpy().copy() if rank == 0 else None))
+        q.put((rank, pg.bounds, out3.numpy().copy() if rank == host else None))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,rho", [(2, 0.2), (3, 0.6), (2, 0.0)])
-def test_pipelined_gather_schedule(oracle, world, rho):
+@pytest.mark.parametrize("world,rho,host", [(2, 0.2, 0), (3, 0.6, 0), (2, 0.0, 0), (3, 0.3, 2), (2, 0.2, 1)])
+def test_pipelined_gather_schedule(oracle, world, rho, host):
     """Uneven row split + chunked send/recv + host-rank expansion reproduce the whole matrix."""
     n, k = 999, 15
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_pipe_worker, args=(r, world, port, n, k, rho, q)) for r in range(world)]
+    procs = [ctx.Process(target=_pipe_worker, args=(r, world, port, n, k, rho, host, q)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=180) for _ in range(world)]
@@ -132,10 +132,12 @@ def test_pipelined_gather_schedule(oracle, world, rho):
     want = oracle.parallel(synth.to_r_matrix(synth.knn_index(n, k, seed=3)))
     for rank, bounds, out in got:
         assert bounds[0][0] == 0 and bounds[-1][1] == n and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
-        if rank == 0:
+        if rank == host:
             assert np.array_equal(out.T, want)
+        else:
+            assert out is None
     if rho >= 0.5 and world == 3:
-        assert got[0][1][0] == (0, 0)  # the host rank only expands
+        assert got[0][1][host] == (0, 0) or got[0][1][host][0] == got[0][1][host][1]  # the host rank only expands
 
 
 def test_weighted_bounds():
