@@ -30,7 +30,7 @@ PROTOTYPES = {
     "gficf_cuda_host_unregister": (C.c_int, [_vp]),
     "gficf_cuda_release": (C.c_int, []),
     "gficf_cuda_last_timings": (C.c_int, [_dp]),
-    "gficf_cuda_last_output": (C.c_int, [C.POINTER(C.c_int32), _dp, _dp]),
+    "gficf_cuda_last_output": (C.c_int, [C.POINTER(C.c_int32), _dp, _dp, _dp]),
     "gficf_cuda_expand_host": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int32, _vp, C.c_int64, C.c_int64, _vp,
                                          C.c_int32]),
     "gficf_cuda_comm_unique_id": (C.c_int, [_vp]),
@@ -65,8 +65,10 @@ PROTOTYPES = {
     "gficf_cuda_jaccard_counts_mutual_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _vp,
                                                        _vp, _vp]),
     "gficf_cuda_snn_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
-    "gficf_cuda_snn_lower_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp,
-                                           _vp]),
+    "gficf_cuda_snn_lower_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp,
+                                           _vp, _vp]),
+    "gficf_cuda_snn_lower": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int32, _vp, _vp, _vp, C.c_int64, _vp,
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]),
     "gficf_cuda_last_launch": (C.c_int, [C.POINTER(C.c_int32)] * 4),
     "gficf_cuda_version": (C.c_char_p, []),
 }

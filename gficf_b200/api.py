@@ -135,7 +135,7 @@ def last_timings() -> dict:
 def last_output() -> dict:
     """How the last host-buffer call produced its output columns (include/gficf_cuda.h,
     gficf_cuda_last_output): mode dma / host / hybrid, share written by host threads, PCIe bytes."""
-    mode, share, nbytes = C.c_int32(0), C.c_double(0), C.c_double(0)
-    _lib.check(_lib.lib().gficf_cuda_last_output(C.byref(mode), C.byref(share), C.byref(nbytes)))
+    mode, share, nbytes, hbytes = C.c_int32(0), C.c_double(0), C.c_double(0), C.c_double(0)
+    _lib.check(_lib.lib().gficf_cuda_last_output(C.byref(mode), C.byref(share), C.byref(nbytes), C.byref(hbytes)))
     return {"mode": {1: "dma", 2: "host", 3: "hybrid"}.get(mode.value, str(mode.value)),
-            "host_share": share.value, "d2h_bytes": nbytes.value}
+            "host_share": share.value, "d2h_bytes": nbytes.value, "h2d_bytes": hbytes.value}

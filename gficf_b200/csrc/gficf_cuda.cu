@@ -81,6 +81,7 @@ thread_local double tl_timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 struct OutputInfo {
   int mode = 1;           // OutMode of the last host-buffer call
   double host_share = 0;  // share of the output pieces written by host threads
+  double h2d_bytes = 0;   // bytes copied host -> device
 };
 thread_local OutputInfo tl_output;
 
@@ -533,12 +534,16 @@ struct Piece {
   cudaEvent_t wait_before;
 };
 
-void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cudaStream_t st) {
+// narrow (host -> device only): the source holds ids as doubles; the workers convert every piece to
+// int32 inside its pinned slot (gficf_host::f64_to_i32) and the copy engine moves HALF the bytes;
+// Seg.bytes / Piece.bytes count SOURCE bytes, Seg.dev addresses the int32 destination.
+void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cudaStream_t st,
+                 bool narrow = false) {
   std::vector<Piece> pieces;
   for (const Seg& g : segs) {
     bool first = true;
     for (size_t off = 0; off < g.bytes; off += kStageChunk) {
-      pieces.push_back({g.host + off, g.dev + off, std::min(kStageChunk, g.bytes - off),
+      pieces.push_back({g.host + off, g.dev + (narrow ? off / 2 : off), std::min(kStageChunk, g.bytes - off),
                         first ? g.wait_before : nullptr});
       first = false;
     }
@@ -555,7 +560,7 @@ void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cud
   std::atomic<int> next(0);
   std::atomic<bool> failed(false);
   const int dev = ws.dev;
-  const int nthreads = std::min(copy_threads(), np);
+  const int nthreads = std::min(narrow ? expand_threads() : copy_threads(), np);
   auto worker = [&]() {
     cudaSetDevice(dev);
     for (;;) {
@@ -572,7 +577,8 @@ void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cud
           }
           if (cudaEventSynchronize(ws.ev_slot[j % kStageSlots]) != cudaSuccess) failed.store(true);
         }
-        memcpy(slot, pc.host, pc.bytes);
+        if (narrow) gficf_host::f64_to_i32((const double*)pc.host, (int32_t*)slot, pc.bytes / 8);
+        else memcpy(slot, pc.host, pc.bytes);
         host_done[j].store(1, std::memory_order_release);
       } else {
         while (!dma_issued[j].load(std::memory_order_acquire)) {
@@ -596,7 +602,8 @@ void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cud
     if (to_device) {
       while (!host_done[j].load(std::memory_order_acquire) && !failed.load()) std::this_thread::yield();
       if (failed.load()) break;
-      if (err == cudaSuccess) err = cudaMemcpyAsync(pc.dev, slot, pc.bytes, cudaMemcpyHostToDevice, st);
+      if (err == cudaSuccess)
+        err = cudaMemcpyAsync(pc.dev, slot, narrow ? pc.bytes / 2 : pc.bytes, cudaMemcpyHostToDevice, st);
     } else {
       // the slot is free once piece j - kStageSlots has been copied out by a worker
       if (j >= kStageSlots)
@@ -623,22 +630,38 @@ void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cud
 // Host -> device of a strided 2-D block (rows x cols doubles, source leading dimension ld_src,
 // destination dense with leading dimension rows).  Pinned sources go straight to the copy
 // engine; pageable ones through staged_copy.
-void h2d_block(DeviceWs& ws, const void* src_v, long long ld_src, void* dst_v, long long rows, int cols,
-               size_t elem, cudaStream_t st) {
-  if (rows <= 0 || cols <= 0) return;
+// Returns the element size of the device copy: an f64 matrix above kSmallCopyBytes arrives as int32
+// (narrowed on the host while it streams: half the PCIe bytes), everything else as it is.
+bool h2d_narrow_enabled() {
+  const char* e = getenv("GFICF_CUDA_H2D_NARROW");
+  return !(e && e[0] == '0');
+}
+
+size_t h2d_block(DeviceWs& ws, const void* src_v, long long ld_src, void* dst_v, long long rows, int cols,
+                 size_t elem, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return elem;
   const char* src = (const char*)src_v;
   char* dst = (char*)dst_v;
-  if (is_pinned(src) || (size_t)rows * cols * elem <= kSmallCopyBytes) {
+  const bool small = (size_t)rows * cols * elem <= kSmallCopyBytes;
+  if (elem == 8 && !small && h2d_narrow_enabled()) {
+    std::vector<Seg> segs;
+    for (int c = 0; c < cols; ++c)
+      segs.push_back({(char*)(src + (size_t)c * ld_src * 8), dst + (size_t)c * rows * 4, (size_t)rows * 8, nullptr});
+    staged_copy(ws, segs, true, st, true);
+    return 4;
+  }
+  if (is_pinned(src) || small) {
     // pinned: straight to the copy engine; small: the driver's own staging beats spinning up threads
     CU_TRY(cudaMemcpy2DAsync(dst, rows * elem, src, ld_src * elem, rows * elem, cols, cudaMemcpyHostToDevice,
                              st));
-    return;
+    return elem;
   }
   std::vector<Seg> segs;
   for (int c = 0; c < cols; ++c)
     segs.push_back({(char*)(src + (size_t)c * ld_src * elem), dst + (size_t)c * rows * elem,
                     (size_t)rows * elem, nullptr});
   staged_copy(ws, segs, true, st);
+  return elem;
 }
 
 // Device -> host of contiguous runs (each optionally behind an event).  Pinned destinations:
@@ -663,6 +686,7 @@ struct SlabResult {
   float ms_h2d = 0, ms_k0 = 0, ms_k1 = 0, ms_d2h = 0, ms_gather = 0;
   int launches = 0;
   double d2h_bytes = 0;       // bytes that crossed PCIe towards the host
+  double h2d_bytes = 0;       // ... and towards the device
   int out_mode = kOutDma;     // how the output columns were produced (OutMode)
   double host_items = 0;      // share of the output pieces written by host threads
   bool counts_ready = false;  // phase 1 left fast-kernel counts in ws.counts
@@ -813,10 +837,11 @@ void device_phase0(Slab s, SlabResult* res) {
     unsigned* d_flags = (unsigned*)ws.small.p;
     CU_TRY(cudaMemsetAsync(ws.small.p, 0, 64, ws.s_comp));
     CU_TRY(cudaEventRecord(ws.ev[0], ws.s_comp));
-    h2d_block(ws, (const char*)s.h_idx + (size_t)s.lo * s.elem, s.n, ws.in_raw.p, s.rows, k, s.elem,
-              ws.s_comp);
+    const size_t dev_elem = h2d_block(ws, (const char*)s.h_idx + (size_t)s.lo * s.elem, s.n, ws.in_raw.p,
+                                      s.rows, k, s.elem, ws.s_comp);
+    res->h2d_bytes = (double)s.rows * k * dev_elem;
     CU_TRY(cudaEventRecord(ws.ev[1], ws.s_comp));
-    if (s.elem == 8)
+    if (dev_elem == 8)
       launch_layout((const double*)ws.in_raw.p, s.rows, s.lo, s.n, k, s.lo, s.hi, (int*)ws.idx.p, d_flags,
                     ws.s_comp);
     else
@@ -1107,10 +1132,11 @@ int gficf_cuda_last_timings(double* ms8) {
   return GFICF_OK;
 }
 
-int gficf_cuda_last_output(int32_t* out_mode, double* host_share, double* d2h_bytes) {
+int gficf_cuda_last_output(int32_t* out_mode, double* host_share, double* d2h_bytes, double* h2d_bytes) {
   if (out_mode) *out_mode = tl_output.mode;
   if (host_share) *host_share = tl_output.host_share;
   if (d2h_bytes) *d2h_bytes = tl_timings[7];
+  if (h2d_bytes) *h2d_bytes = tl_output.h2d_bytes;
   return GFICF_OK;
 }
 
@@ -1245,7 +1271,9 @@ int jaccard_host_call(const void* idx, int elem, int64_t n, int32_t k, double* o
     tm[6] += r.launches;
     tm[7] += r.d2h_bytes;
   }
-  tl_output = {res[0].out_mode, res[0].host_items};
+  double h2d_total = 0;
+  for (auto& r : res) h2d_total += r.h2d_bytes;
+  tl_output = {res[0].out_mode, res[0].host_items, h2d_total};
   tm[4] = std::chrono::duration<double, std::milli>(t1 - t0).count();
   memcpy(tl_timings, tm, sizeof tm);
   if (flags & kFlagBadId)
@@ -1374,7 +1402,7 @@ int gficf_cuda_jaccard_rank(const double* idx, int64_t n, int32_t k, double* out
                   std::chrono::duration<double, std::milli>(t1 - t0).count(), res.ms_gather,
                   (double)res.launches, res.d2h_bytes};
   memcpy(tl_timings, tm, sizeof tm);
-  tl_output = {res.out_mode, res.host_items};
+  tl_output = {res.out_mode, res.host_items, res.h2d_bytes};
   return GFICF_OK;
   API_END
 }
@@ -1608,45 +1636,195 @@ int gficf_cuda_jaccard_counts_mutual_dev(const int32_t* d_idx_i32, int64_t n, in
   DEV_END
 }
 
+// scratch layout of gficf_cuda_snn_lower_dev (all pieces 256-byte aligned)
+struct SnnScratch {
+  int *act, *vid, *cnt_b, *cnt, *cursor, *big_cols, *n_big;
+  unsigned* first;
+  long long *off_a, *off_b, *block_sums, *total, *nv;
+  gficf::SnnEntry* entries;
+  size_t bytes;
+};
+static SnnScratch snn_scratch_layout(char* base, int64_t n, int64_t cap) {
+  SnnScratch s;
+  size_t off = 0;
+  auto take = [&](size_t b) {
+    char* p = base + off;
+    off += (b + 255) / 256 * 256;
+    return p;
+  };
+  const size_t nb = (size_t)((n + gficf::kScanBlock - 1) / gficf::kScanBlock + 2);
+  s.act = (int*)take((size_t)n * 4);
+  s.vid = (int*)take((size_t)n * 4);
+  s.first = (unsigned*)take((size_t)n * 4);
+  s.cnt_b = (int*)take((size_t)n * 4);
+  s.cnt = (int*)take((size_t)n * 4);
+  s.cursor = (int*)take((size_t)n * 4);
+  s.big_cols = (int*)take((size_t)(cap / gficf::kSnnWarpRankMax + 2) * 4);
+  s.n_big = (int*)take(4);
+  s.off_a = (long long*)take((size_t)(n + 1) * 8);
+  s.off_b = (long long*)take((size_t)(n + 1) * 8);
+  s.block_sums = (long long*)take(nb * 8);
+  s.total = (long long*)take(8);
+  s.nv = (long long*)take(8);
+  s.entries = (gficf::SnnEntry*)take((size_t)cap * sizeof(gficf::SnnEntry));
+  s.bytes = off;
+  return s;
+}
+
 size_t gficf_cuda_snn_scratch_bytes(int64_t n, int64_t cap) {
   if (n < 0 || cap < 0) return 0;
-  const size_t nb = (size_t)((n + kScanBlock - 1) / kScanBlock + 2);
-  // counts[n] | cursor[n] | block sums | total | staged entries[cap] (16 B each)
-  return (size_t)n * 8 + nb * 8 + 64 + (size_t)cap * 16 + 256;
+  return snn_scratch_layout(nullptr, n, cap).bytes;
 }
 
 int gficf_cuda_snn_lower_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, const uint8_t* d_um,
                              int64_t* d_colptr, int32_t* d_row, double* d_w, int64_t cap,
-                             void* d_scratch, uint32_t* d_flags, void* stream) {
+                             int32_t* d_vertex_cell, int64_t* d_n_vertices, void* d_scratch,
+                             uint32_t* d_flags, void* stream) {
   DEV_BEGIN
   if (!d_idx_i32 || !d_um || !d_colptr || !d_row || !d_w || !d_scratch || !d_flags || n < 1 || k < 1)
     return GFICF_E_ARG;
-  if (k > 127 || n >= 0x7fffffffLL) return GFICF_E_LIMIT;
+  if (k > 127 || n >= 0x7fffffffLL || n * (long long)k >= 0xffffffffLL) return GFICF_E_LIMIT;
   if (cap < n * (int64_t)k) return GFICF_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int kp = row_stride(k);
   const long long nb = (n + kScanBlock - 1) / kScanBlock;
-  char* sc = (char*)d_scratch;
-  int* cnt = (int*)sc;
-  int* cursor = cnt + n;
-  long long* block_sums = (long long*)(sc + (((size_t)n * 8 + 63) / 64) * 64);
-  long long* total = block_sums + nb + 1;
-  char* tmp = (char*)(total + 1);
-  tmp = (char*)((((uintptr_t)tmp + 63) / 64) * 64);
-  SnnEntry* entries = (SnnEntry*)tmp;  // [cap]
-  CU_TRY(cudaMemsetAsync(cnt, 0, (size_t)n * 8, st));  // counts and cursors
-  const int grid = grid_1d(n * 32, 256, 8);
-  snn_edges_kernel<false><<<grid, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, cnt, nullptr, nullptr, d_flags);
-  scan_block_sums_kernel<<<(int)nb, kScanBlock, 0, st>>>(cnt, n, block_sums);
-  compact_scan_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
-  scan_finish_kernel<<<(int)nb, kScanBlock, 0, st>>>(cnt, n, block_sums, total, (long long*)d_colptr);
-  snn_edges_kernel<true><<<grid, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, cursor, (const long long*)d_colptr,
-                                              entries, d_flags);
-  snn_rank_sort_kernel<<<grid_1d(n * (long long)k, 256, 8), 256, 0, st>>>(
-      (const long long*)d_colptr, total, entries, d_row, d_w);
+  const SnnScratch sc = snn_scratch_layout((char*)d_scratch, n, cap);
+  long long* d_nv = d_n_vertices ? (long long*)d_n_vertices : sc.nv;
+  auto scan = [&](const int* cnt, long long* out) {  // exclusive scan, out[n] = total
+    scan_block_sums_kernel<<<(int)nb, kScanBlock, 0, st>>>(cnt, n, sc.block_sums);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(sc.block_sums, nb, sc.total);
+    scan_finish_kernel<<<(int)nb, kScanBlock, 0, st>>>(cnt, n, sc.block_sums, sc.total, out);
+  };
+  const int grid_w = grid_1d(n * 32, 256, 8);  // warp per row / column
+  const int grid_t = grid_1d(n, 256, 8);
+  // cnt_b, cnt, cursor, big_cols, n_big are contiguous in the layout: one memset
+  CU_TRY(cudaMemsetAsync(sc.cnt_b, 0, (size_t)((char*)sc.off_a - (char*)sc.cnt_b), st));
+  CU_TRY(cudaMemsetAsync(sc.first, 0xff, (size_t)n * 4, st));
+  // 1. igraph's vertex numbering (first appearance in c(from, to) of the kept rows)
+  snn_active_kernel<<<grid_w, 256, 0, st>>>(d_um, n, k, sc.act, d_flags);
+  scan(sc.act, sc.off_a);
+  snn_vertex_ids_kernel<<<grid_t, 256, 0, st>>>(n, sc.act, sc.off_a, sc.off_b, sc.vid, 0, nullptr, d_nv);
+  snn_targets_kernel<0><<<grid_w, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, sc.act, sc.off_a, sc.first, sc.cnt_b,
+                                               sc.off_b, sc.vid);
+  snn_targets_kernel<1><<<grid_w, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, sc.act, sc.off_a, sc.first, sc.cnt_b,
+                                               sc.off_b, sc.vid);
+  scan(sc.cnt_b, sc.off_b);
+  snn_targets_kernel<2><<<grid_w, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, sc.act, sc.off_a, sc.first, sc.cnt_b,
+                                               sc.off_b, sc.vid);
+  snn_vertex_ids_kernel<<<grid_t, 256, 0, st>>>(n, sc.act, sc.off_a, sc.off_b, sc.vid, 1,
+                                                (int*)d_vertex_cell, d_nv);
+  // 2. entries per column, column pointers, scatter, rows ascending inside a column
+  snn_edges_kernel<false><<<grid_w, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, sc.vid, sc.cnt, nullptr, nullptr);
+  scan(sc.cnt, (long long*)d_colptr);
+  snn_edges_kernel<true><<<grid_w, 256, 0, st>>>(d_idx_i32, d_um, n, k, kp, sc.vid, sc.cursor,
+                                                (const long long*)d_colptr, sc.entries);
+  snn_sort_columns_kernel<<<grid_w, 256, 0, st>>>((const long long*)d_colptr, d_nv, sc.entries, d_row, d_w,
+                                                  sc.big_cols, sc.n_big);
+  static thread_local bool attr_set[64] = {};
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  const int big_smem = kSnnSmemSortMax * 12;
+  if (!attr_set[dev & 63]) {
+    CU_TRY(cudaFuncSetAttribute(snn_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem));
+    attr_set[dev & 63] = true;
+  }
+  snn_sort_big_kernel<<<sm_count() * 2, 256, big_smem, st>>>((const long long*)d_colptr, sc.entries, d_row, d_w,
+                                                           sc.big_cols, sc.n_big);
   CU_TRY(cudaGetLastError());
   return GFICF_OK;
   DEV_END
+}
+
+int gficf_cuda_snn_lower(const void* idx_colmajor, int32_t elem_bytes, int64_t n, int32_t k,
+                         int64_t* colptr, int32_t* row, double* w, int64_t cap, int32_t* vertex_cell,
+                         int64_t* n_vertices, int64_t* nnz, char* err, size_t errlen) {
+  API_BEGIN
+  if (err && errlen) err[0] = 0;
+  if (nnz) *nnz = 0;
+  if (n_vertices) *n_vertices = 0;
+  if (n < 0 || k < 0 || (elem_bytes != 8 && elem_bytes != 4)) throw Err{GFICF_E_ARG, "bad matrix description"};
+  if (n == 0 || k == 0) return GFICF_OK;
+  if (!idx_colmajor || !colptr || !row || !w || cap < 0) throw Err{GFICF_E_ARG, "null output pointer"};
+  if (k > 127) throw Err{GFICF_E_LIMIT, "the graph build carries the mutual flag in bit 7 of the count byte: k <= 127"};
+  if (n >= 0x7fffffffLL - 2 || (long double)n * k >= 2147483647.0L)
+    throw Err{GFICF_E_LIMIT, "n*k must stay below 2^31 (the reference's int row index)"};
+  if (visible_devices() < 1) throw Err{GFICF_E_CUDA, "no CUDA device is visible (this path has no CPU fallback)"};
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  const auto t0 = std::chrono::steady_clock::now();
+  DeviceWs& ws = g_ws[0];
+  CU_TRY(cudaSetDevice(0));
+  ws.ensure(0);
+  g_active_devices.store(1);
+  const long long E = (long long)n * k;
+  const int kp = row_stride(k);
+  ws.in_raw.need((size_t)E * elem_bytes);
+  ws.idx.need((size_t)n * kp * sizeof(int));
+  ws.counts.need((size_t)E);
+  ws.scratch.need(gficf_cuda_snn_scratch_bytes(n, E));
+  // results on the device: colptr | w | row | vertex map
+  const size_t o_w = ((size_t)(n + 1) * 8 + 255) / 256 * 256, o_row = o_w + (size_t)E * 8,
+               o_vc = o_row + ((size_t)E * 4 + 255) / 256 * 256;
+  ws.out.need(o_vc + (size_t)n * 4);
+  char* d_res = (char*)ws.out.p;
+  unsigned* d_flags = (unsigned*)ws.small.p;
+  long long* d_nv = (long long*)((char*)ws.small.p + 16);
+  CU_TRY(cudaMemsetAsync(ws.small.p, 0, 64, ws.s_comp));
+  CU_TRY(cudaEventRecord(ws.ev[0], ws.s_comp));
+  const size_t dev_elem = h2d_block(ws, idx_colmajor, n, ws.in_raw.p, n, k, (size_t)elem_bytes, ws.s_comp);
+  CU_TRY(cudaEventRecord(ws.ev[1], ws.s_comp));
+  if (dev_elem == 8)
+    launch_layout((const double*)ws.in_raw.p, n, 0, n, k, 0, n, (int*)ws.idx.p, d_flags, ws.s_comp);
+  else
+    launch_layout((const int*)ws.in_raw.p, n, 0, n, k, 0, n, (int*)ws.idx.p, d_flags, ws.s_comp);
+  CU_TRY(cudaEventRecord(ws.ev[2], ws.s_comp));
+  if (!launch_fast<2>((const int*)ws.idx.p, k, 0, n, nullptr, nullptr, nullptr, ws.counts.p, d_flags, ws.s_comp))
+    throw Err{GFICF_E_LIMIT, "k outside the range of the mutual-bit count kernel"};
+  const int rc = gficf_cuda_snn_lower_dev((const int32_t*)ws.idx.p, n, k, (const uint8_t*)ws.counts.p,
+                                          (int64_t*)d_res, (int32_t*)(d_res + o_row), (double*)(d_res + o_w), E,
+                                          (int32_t*)(d_res + o_vc), (int64_t*)d_nv, ws.scratch.p, d_flags, ws.s_comp);
+  if (rc != GFICF_OK) throw Err{rc, "graph kernels could not be launched"};
+  CU_TRY(cudaEventRecord(ws.ev[3], ws.s_comp));
+  // flags, vertex count and entry count decide what is copied back
+  CU_TRY(cudaMemcpyAsync(ws.h_small, ws.small.p, 32, cudaMemcpyDeviceToHost, ws.s_comp));
+  CU_TRY(cudaMemcpyAsync((char*)ws.h_small + 32, d_res + (size_t)n * 8, 8, cudaMemcpyDeviceToHost, ws.s_comp));
+  CU_TRY(cudaStreamSynchronize(ws.s_comp));
+  const unsigned flags = ws.h_small[0];
+  const long long nv = *(long long*)((char*)ws.h_small + 16), total = *(long long*)((char*)ws.h_small + 32);
+  cudaSetDevice(prev_dev);
+  if (flags & kFlagBadId)
+    throw Err{GFICF_E_RANGE,
+              "neighbour ids must be integers in [1, nrow] (NaN, fractional or out-of-range id found)"};
+  if (flags & (kFlagDupId | kFlagHashFail))
+    throw Err{GFICF_E_LIMIT, "a row lists an id twice: the device graph build needs distinct ids per row"};
+  if (nnz) *nnz = total;
+  if (n_vertices) *n_vertices = nv;
+  if (total > cap) throw Err{GFICF_E_ARG, fmt("row / w capacity %lld is below the %lld entries of the graph", (long long)cap, total)};
+  CU_TRY(cudaSetDevice(0));
+  std::vector<Seg> segs;
+  segs.push_back({(char*)colptr, d_res, (size_t)(n + 1) * 8, nullptr});
+  if (total) {
+    segs.push_back({(char*)row, d_res + o_row, (size_t)total * 4, nullptr});
+    segs.push_back({(char*)w, d_res + o_w, (size_t)total * 8, nullptr});
+  }
+  if (vertex_cell && nv) segs.push_back({(char*)vertex_cell, d_res + o_vc, (size_t)nv * 4, nullptr});
+  CU_TRY(cudaEventRecord(ws.ev[4], ws.s_copy));
+  d2h_segs(ws, segs, ws.s_copy);
+  CU_TRY(cudaEventRecord(ws.ev[5], ws.s_copy));
+  CU_TRY(cudaStreamSynchronize(ws.s_copy));
+  float ms[4] = {0, 0, 0, 0};
+  CU_TRY(cudaEventElapsedTime(&ms[0], ws.ev[0], ws.ev[1]));
+  CU_TRY(cudaEventElapsedTime(&ms[1], ws.ev[1], ws.ev[2]));
+  CU_TRY(cudaEventElapsedTime(&ms[2], ws.ev[2], ws.ev[3]));
+  CU_TRY(cudaEventElapsedTime(&ms[3], ws.ev[4], ws.ev[5]));
+  cudaSetDevice(prev_dev);
+  double tm[8] = {ms[0], ms[1], ms[2], ms[3],
+                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), 0, 22,
+                  (double)(n + 1) * 8 + (double)total * 12 + (vertex_cell ? (double)nv * 4 : 0.0)};
+  memcpy(tl_timings, tm, sizeof tm);
+  return GFICF_OK;
+  API_END
 }
 
 }  // extern "C"

@@ -41,6 +41,10 @@ void expand_rows(const ExpandJob& job, long long row_lo, long long row_hi);
 // memcpy whose destination is written with non-temporal stores (large, write-once destinations)
 void stream_copy(void* dst, const void* src, size_t bytes);
 
+// ids held as doubles -> int32 (exact for valid ids; NaN / fractional / out-of-int32-range -> 0,
+// which the device pre-pass rejects): the host half of the compressing H2D
+void f64_to_i32(const double* src, int32_t* dst, size_t count);
+
 // "avx512" / "avx2" / "scalar": which body expand_rows dispatches to on this CPU
 const char* isa();
 

@@ -121,11 +121,13 @@ int gficf_cuda_last_timings(double* ms8);
  * 1-byte intersection counts crossed PCIe; host threads wrote from = i+1, to = idx(i,j),
  * weight = table[u] straight into the caller's matrix, bit-identical by construction), 3 = hybrid
  * (both at once, (column, row-chunk) pieces claimed dynamically); *host_share = share of the pieces
- * written by host threads; *d2h_bytes = bytes that crossed PCIe towards the host.  The mode is chosen
+ * written by host threads; *d2h_bytes / *h2d_bytes = bytes that crossed PCIe towards the host / the
+ * device (an f64 matrix is narrowed to int32 on the host while it streams -- its values are integer
+ * ids -- so it costs 4 bytes per id; GFICF_CUDA_H2D_NARROW=0 sends the doubles).  The mode is chosen
  * per call: hybrid for page-locked output, host for pageable output (what R passes), dma for k > 255
  * or the serial export; GFICF_CUDA_OUT_MODE=dma|host|hybrid overrides, GFICF_CUDA_EXPAND_THREADS
  * sets the number of host threads. */
-int gficf_cuda_last_output(int32_t* out_mode, double* host_share, double* d2h_bytes);
+int gficf_cuda_last_output(int32_t* out_mode, double* host_share, double* d2h_bytes, double* h2d_bytes);
 
 /* The host half of the counts-over-PCIe output on its own: rows [row_lo,row_hi) of the fixed-slot
  * export written into out_colmajor ((n*k) x 3) from the caller's matrix (elem_bytes 8 = double,
@@ -278,18 +280,35 @@ size_t gficf_cuda_expand_scratch_bytes(int64_t slab_edges);
  * reads.  Replaces, on the device, relations[relations[,3]>0,] + igraph::graph.data.frame +
  * as_adjacency_matrix (parallel edges summed) of R/clustCells.R:66-69,81 and the strictly-lower-
  * triangle scan of src/RModularityOptimizer.cpp:67-83. ---- */
-#define GFICF_FLAG_ISOLATED 16u /* some cell has no edge with u>0: igraph would number vertices differently */
+#define GFICF_FLAG_ISOLATED 16u /* informational: some cell keeps no edge of its own (u == 0 on its whole row) */
 /* Count kernel that also sets bit 7 of an edge's byte when the edge is mutual (i is in N(t)); k <= 127. */
 int gficf_cuda_jaccard_counts_mutual_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
                                          int64_t row_hi, uint8_t* d_um, uint32_t* d_flags, void* stream);
-/* CSC of the strictly lower triangle of the symmetric weighted adjacency matrix: d_colptr[n+1]
- * (int64), d_row / d_w with capacity cap >= n*k entries, rows ascending inside a column
- * (column = node1, row = node2 of the reference's edge list).  d_um covers all n rows.
- * Valid when *d_flags stays free of GFICF_FLAG_DUP_ID / _HASH_FAIL / _ISOLATED. */
+/* CSC of the strictly lower triangle of the symmetric weighted adjacency matrix over igraph's vertex
+ * numbering (first appearance in c(from, to) of the kept rows: cells with an edge of their own in
+ * cell order, then cells that only appear as targets in order of the first edge naming them; cells
+ * in no kept edge are not vertices):
+ *   d_colptr[n+1] (int64; entries beyond the vertex count repeat the total), d_row / d_w with capacity
+ *   cap >= n*k entries, rows ascending inside a column (column = node1, row = node2 of the
+ *   reference's edge list, both vertex ids), d_vertex_cell[n] (vertex id -> 1-based cell id; may be
+ *   NULL), *d_n_vertices (device int64; may be NULL).  d_um covers all n rows.
+ * Valid when *d_flags stays free of GFICF_FLAG_DUP_ID / _HASH_FAIL. */
 size_t gficf_cuda_snn_scratch_bytes(int64_t n, int64_t cap);
 int gficf_cuda_snn_lower_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, const uint8_t* d_um,
                              int64_t* d_colptr, int32_t* d_row, double* d_w, int64_t cap,
-                             void* d_scratch, uint32_t* d_flags, void* stream);
+                             int32_t* d_vertex_cell, int64_t* d_n_vertices, void* d_scratch,
+                             uint32_t* d_flags, void* stream);
+/* The same step on HOST buffers, from the caller's kNN matrix (elem_bytes 8 = double, 4 = int32;
+ * column-major, 1-based) to the arrays RunModularityClusteringCpp's edge-list loop produces
+ * (src/RModularityOptimizer.cpp:67-88): H2D, layout pre-pass, count kernel with the mutual bit, the
+ * graph kernels, D2H of colptr / row / weight / vertex map -- 12 bytes per undirected edge instead of
+ * the 24 bytes per directed edge slot of the edge matrix.  colptr has n+1 entries (the first
+ * *n_vertices + 1 are meaningful), row / w have capacity cap (n*k always suffices); *nnz receives
+ * the number of entries.  GFICF_E_LIMIT: k > 127 or a row lists an id twice (use gficf_cuda_jaccard
+ * and the host graph build there).  One device. */
+int gficf_cuda_snn_lower(const void* idx_colmajor, int32_t elem_bytes, int64_t n, int32_t k,
+                         int64_t* colptr, int32_t* row, double* w, int64_t cap, int32_t* vertex_cell,
+                         int64_t* n_vertices, int64_t* nnz, char* err, size_t errlen);
 
 /* Launch geometry of the last fast-kernel launch on this thread (for the
  * bench record): grid, block, dynamic smem bytes, kernels launched. */

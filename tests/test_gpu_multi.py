@@ -136,6 +136,20 @@ if rank == 0:
 peer.close()
 del o3, padded, idx0
 torch.cuda.empty_cache()
+# the step after the path, row-sharded: per-rank counts with the mutual bit, all-gather, graph build on the host rank
+from gficf_b200 import snn
+for n, k, fam in ((120_000, 30, "planted"), (9_000, 6, "uniform")):
+    idx0 = synth.knn_index(n, k, family=fam, scramble=True, device="cuda")
+    padded, fl = D.pad_rows(idx0)
+    res = snn.snn_lower_triangle_sharded(padded, n, k)
+    if rank == 0:
+        one = snn.snn_lower_triangle(padded, n, k, with_vertex_map=True)
+        for a_, b_ in zip(res[:4], one[:4]):
+            assert torch.equal(a_, b_), ("snn sharded", n, k)
+        assert int(res[4][0]) & ~16 == 0
+    else:
+        assert res is None
+    dist.barrier()
 # the library's own one-rank-per-GPU entry on shared page-locked host matrices
 from gficf_b200 import multiproc
 multiproc.comm_init_from_torch()
