@@ -370,6 +370,10 @@ def run_ours(a):
         dist.broadcast(cal, src=0)  # every rank must use the same split
         t_fused, t_count, t_expand = (float(x) for x in cal)
         share = a.host_share if a.host_share >= 0 else sharding.balanced_host_share(world, t_fused, t_count, t_expand)
+        if a.host_share < 0 and share < 0.08:
+            # measured (profiles/r02_scaling.md): a host rank that first spends a few % of the step on
+            # own rows starts its streaming expand behind the peers and ends later than one that only expands
+            share = 0.0
         if a.gather == "peer" and k <= 127:
             try:
                 pg = sharding.PeerGather(n, k, host_share=share)
@@ -416,6 +420,8 @@ def run_ours(a):
         step()
     barrier()
     launches0 = pg.launches if pg is not None else 0
+    if pg is not None and hasattr(pg, "trace") and rank == 0:
+        pg.trace = []
     sampler = ClockSampler(local)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
@@ -433,7 +439,16 @@ def run_ours(a):
     clocks = sampler.stop()
     step_ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in zip(ev0, ev1)], dtype=torch.float64, device=dev)
     gather_flags = 0
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([float(step_ms.mean())], dtype=torch.float64, device=dev)
+        allm = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        per_rank = {"step_ms_mean": [round(float(v[0]), 4) for v in allm]}
+        if rank == 0 and getattr(pg, "trace", None):
+            tr = pg.trace
+            per_rank["host_rank_own_rows_ms"] = round(sum(a.elapsed_time(b) for a, b, _ in tr) / len(tr), 4)
+            per_rank["host_rank_expand_ms"] = round(sum(b.elapsed_time(c) for _, b, c in tr) / len(tr), 4)
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # max over ranks, per step
         nl = pg.launches - launches0
         if a.gather == "peer":
@@ -514,7 +529,8 @@ def run_ours(a):
             out_host = gficf_b200.pinned_empty((E, 3))
             gficf_b200.rcpp_parallel_jaccard_coef(r_host, False, 1, out=out_host)
             dt, tm, om = timed_call(r_host, out_host, e2e_steps)
-            e2e = {"value": E / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": int(om["d2h_bytes"]),
+            e2e = {"value": E / dt, "unit": UNIT, "h2d_bytes_per_step": int(om["h2d_bytes"]),
+                   "d2h_bytes_per_step": int(om["d2h_bytes"]),
                    "ms_per_step": dt * 1e3, "call": "gficf_b200.rcpp_parallel_jaccard_coef (f64 R matrix, pinned host buffers)",
                    "output_mode": om, "breakdown_ms": tm}
             if parity is not None:
@@ -525,9 +541,11 @@ def run_ours(a):
                 parity["e2e_equals_value_path_full_matrix"] = bool(np.array_equal(oh, dev_res))
                 del dev_res
             # r01's output path for comparison: the device writes 24 B/edge, the copy engine moves them
-            dtd, tmd, omd = timed_call(r_host, out_host, 3, {"GFICF_CUDA_OUT_MODE": "dma"})
-            e2e["dma_output_mode"] = {"value": E / dtd, "ms_per_step": dtd * 1e3, "d2h_bytes_per_step": int(omd["d2h_bytes"]),
-                                      "breakdown_ms": tmd}
+            dtd, tmd, omd = timed_call(r_host, out_host, 3, {"GFICF_CUDA_OUT_MODE": "dma", "GFICF_CUDA_H2D_NARROW": "0"})
+            e2e["dma_output_mode"] = {"value": E / dtd, "ms_per_step": dtd * 1e3, "h2d_bytes_per_step": int(omd["h2d_bytes"]),
+                                      "d2h_bytes_per_step": int(omd["d2h_bytes"]), "breakdown_ms": tmd,
+                                      "what": "r01 path: doubles over PCIe both ways (GFICF_CUDA_OUT_MODE=dma, "
+                                              "GFICF_CUDA_H2D_NARROW=0)"}
             # the same call on ordinary pageable memory (what R hands over)
             r_page = np.asfortranarray(np.array(r_host))
             out_page = np.zeros((E, 3), dtype=np.float64, order="F")
@@ -540,7 +558,7 @@ def run_ours(a):
             r_i32 = gficf_b200.pinned_empty((n, k), dtype=np.int32)
             r_i32[...] = np.asarray(r_host).astype(np.int32)
             dti, tmi, omi = timed_call(r_i32, out_host, 3)
-            e2e["int32_input"] = {"value": E / dti, "ms_per_step": dti * 1e3, "h2d_bytes_per_step": 4 * E,
+            e2e["int32_input"] = {"value": E / dti, "ms_per_step": dti * 1e3, "h2d_bytes_per_step": int(omi["h2d_bytes"]),
                                   "d2h_bytes_per_step": int(omi["d2h_bytes"]), "output_mode": omi, "breakdown_ms": tmi}
             del r_i32, r_host, out_host
         else:
@@ -584,9 +602,9 @@ def run_ours(a):
             dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             om = gficf_b200.last_output()
-            d2h = torch.tensor([om["d2h_bytes"]], dtype=torch.float64, device=dev)
+            d2h = torch.tensor([om["d2h_bytes"], om["h2d_bytes"]], dtype=torch.float64, device=dev)
             dist.all_reduce(d2h)
-            e2e = {"value": E / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": 8 * E,
+            e2e = {"value": E / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": int(d2h[1]),
                    "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": float(dt[0]) * 1e3,
                    "call": "gficf_b200.multiproc.rcpp_parallel_jaccard_coef_rank (one rank per GPU, shared "
                            "page-locked host matrices; each rank moves its own row slab)",
@@ -688,6 +706,7 @@ def run_ours(a):
             "kernel_only": None if world == 1 else {
                 "value": E / (kern_avg_ms * 1e-3), "unit": UNIT, "ms": kern_avg_ms,
                 "what": "all ranks counting their rows concurrently, slowest rank's kernel; no gather / expand"},
+            "per_rank": per_rank,
             "clocks": clocks,
             "gpu_launches": a.steps if world == 1 else int(total_launches),
             "loop_wall_ms": t_wall * 1e3,

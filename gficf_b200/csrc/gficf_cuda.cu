@@ -142,8 +142,14 @@ void launch_small_t(const int* idx, int k, long long lo, long long hi, double* f
   auto kern = jaccard_small_k_kernel<KP, CO, SKIP>;
   const int block = kSmallWarps * 32;
   const int grid = persistent_grid(kern, block, 0, (hi - lo + kSmallWarps - 1) / kSmallWarps);
-  kern<<<grid, block, 0, st>>>(idx, k, lo, hi, f, t, w, u, flags, tag);
-  tl_launch = {grid, block, (int)(sizeof(unsigned) * kSmallWarps * SmallK<KP>::TS + 33 * 8), KP};
+  int lg_group = 0;  // CO == 3: rows per group = 16 / gcd(k, 16), so that a group's bytes are whole 16-byte vectors
+  if (CO == 3)
+    while (((k << lg_group) & 15) != 0) ++lg_group;
+  const long long work = CO == 3 ? (((hi - lo) >> lg_group) + 1 + kSmallWarps - 1) / kSmallWarps
+                                 : (hi - lo + kSmallWarps - 1) / kSmallWarps;
+  const int grid3 = CO == 3 ? persistent_grid(kern, block, 0, work) : grid;
+  kern<<<grid3, block, 0, st>>>(idx, k, lo, hi, f, t, w, u, flags, tag, lg_group);
+  tl_launch = {grid3, block, (int)(sizeof(unsigned) * kSmallWarps * SmallK<KP>::TS + 33 * 8), KP};
 }
 
 // the pad-skipping variant costs registers, so it is used only when a whole 16-byte piece of every
@@ -206,7 +212,8 @@ bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, d
                  void* u_any, unsigned* flags, cudaStream_t st, unsigned tag = 0) {
   uint8_t* u = (uint8_t*)u_any;  // one byte per edge for k <= 255, two above
   if (CO == 2 && k > 127) return false;  // bit 7 of the count byte carries the mutual flag
-  if (tag && (CO != 1 || k > 127)) return false;  // ... or the epoch bit of the streaming gather
+  if (tag && ((CO != 1 && CO != 3) || k > 127)) return false;  // ... or the epoch bit of the streaming gather
+  if (CO == 3 && k > 32) return false;                           // grouped vector stores: the k <= 32 kernel only
   if (hi <= lo) return true;
   const int kp = row_stride(k);
   if (k <= 4) launch_small<4, CO>(idx, k, lo, hi, f, t, w, u, flags, st, tag);
@@ -230,16 +237,29 @@ bool launch_fast(const int* idx, int k, long long lo, long long hi, double* f, d
   return true;
 }
 
-// bounded spins of the peer-memory kernels: GFICF_CUDA_PEER_TIMEOUT_MS (default 20 s) in SM clocks
+// bounded spins of the peer-memory kernels: GFICF_CUDA_PEER_TIMEOUT_MS (default 20 s) in SM clocks.
+// The clock rate is queried once per device: cudaDevAttrClockRate is one of the attributes the
+// driver answers slowly (milliseconds), and this sits on the launch path of every step.
 long long peer_spin_clocks(long long timeout_ms) {
+  static std::atomic<int> khz_cache[64];
+  static std::atomic<long long> env_ms{-1};
   if (timeout_ms <= 0) {
-    const char* e = getenv("GFICF_CUDA_PEER_TIMEOUT_MS");
-    timeout_ms = e ? atoll(e) : 0;
-    if (timeout_ms <= 0) timeout_ms = 20000;
+    long long v = env_ms.load();
+    if (v < 0) {
+      const char* e = getenv("GFICF_CUDA_PEER_TIMEOUT_MS");
+      v = e ? atoll(e) : 0;
+      if (v <= 0) v = 20000;
+      env_ms.store(v);
+    }
+    timeout_ms = v;
   }
-  int dev = 0, khz = 0;
+  int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
-  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+  int khz = khz_cache[dev & 63].load();
+  if (khz <= 0) {
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+    khz_cache[dev & 63].store(khz);
+  }
   return timeout_ms * (long long)khz;
 }
 
@@ -643,7 +663,10 @@ size_t h2d_block(DeviceWs& ws, const void* src_v, long long ld_src, void* dst_v,
   const char* src = (const char*)src_v;
   char* dst = (char*)dst_v;
   const bool small = (size_t)rows * cols * elem <= kSmallCopyBytes;
-  if (elem == 8 && !small && h2d_narrow_enabled()) {
+  // narrowing trades host memory traffic (read 8 + write 4 + DMA read 4 bytes per id instead of a DMA
+  // read of 8) for PCIe bytes: a win while ONE link is the bottleneck, a loss when several GPUs'
+  // links together outrun the host's memory (measured at 8 ranks: 12.4 ms instead of ~3)
+  if (elem == 8 && !small && h2d_narrow_enabled() && g_active_devices.load() * g_sharers.load() == 1) {
     std::vector<Seg> segs;
     for (int c = 0; c < cols; ++c)
       segs.push_back({(char*)(src + (size_t)c * ld_src * 8), dst + (size_t)c * rows * 4, (size_t)rows * 8, nullptr});
@@ -1560,9 +1583,12 @@ int gficf_cuda_jaccard_counts_tagged_dev(const int32_t* d_idx_i32, int64_t n, in
   DEV_BEGIN
   if (!d_idx_i32 || !d_u || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
   if ((tag & ~0x80u) || k > 127) return GFICF_E_LIMIT;
-  if (!launch_fast<1>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u, d_flags,
-                      (cudaStream_t)stream, tag))
-    return GFICF_E_LIMIT;
+  // k <= 32: grouped rows, 16-byte vector stores (d_u is typically a peer GPU's memory)
+  const bool ok = k <= 32 ? launch_fast<3>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u,
+                                           d_flags, (cudaStream_t)stream, tag)
+                          : launch_fast<1>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u,
+                                           d_flags, (cudaStream_t)stream, tag);
+  if (!ok) return GFICF_E_LIMIT;
   return GFICF_OK;
   DEV_END
 }
@@ -1586,9 +1612,11 @@ int gficf_cuda_expand_stream_dev(const int32_t* d_idx_i32, int32_t k, const int6
     ++ns;
   }
   if (!ns) return GFICF_OK;
-  // the resident CTAs (8 per SM) are shared evenly by the segments: every sub-grid then advances
+  // the resident CTAs are shared evenly by the segments: every sub-grid then advances
   // through its segment at the same rate as the ranks that produce the segments
-  long long gx = std::max<long long>(1, (long long)sm_count() * 8 / ns);
+  int per_sm = 0;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_stream_kernel, kExpandThreads, 0));
+  long long gx = std::max<long long>(1, (long long)sm_count() * std::max(1, per_sm) / ns);
   gx = std::min<long long>(gx, (longest + kExpandThreads - 1) / kExpandThreads);
   expand_stream_kernel<<<dim3((unsigned)gx, (unsigned)ns), kExpandThreads, 0, (cudaStream_t)stream>>>(
       d_idx_i32, k, row_stride(k), segs, d_u, d_from, d_to, d_w, tag, peer_spin_clocks(timeout_ms), d_flags);

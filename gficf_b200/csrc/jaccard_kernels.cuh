@@ -234,19 +234,26 @@ struct SmallK {
 
 constexpr int kSmallWarps = GFICF_SMALL_WARPS;
 
-// OUT: 0 = (from,to,w) doubles, 1 = counts, 2 = counts with the mutual-neighbour bit (bit 7)
+// OUT: 0 = (from,to,w) doubles, 1 = counts, 2 = counts with the mutual-neighbour bit (bit 7),
+//      3 = tagged counts for the streaming peer gather: a warp owns GROUPS of 2^lg_group consecutive
+//          rows (group bytes a multiple of 16) and sends a group with 16-byte vector stores -- the
+//          destination is a peer GPU's memory, and NVLink carries a few 128-byte packets per group
+//          instead of one or two 30-byte partial-sector packets per row (measured: 7 peers storing
+//          row by row into one GPU are held to 0.67 ms for a 0.40 ms kernel by the packet rate)
 template <int KP, int OUT, bool SKIP>
 __global__ void __launch_bounds__(kSmallWarps * 32, GFICF_SMALL_MINB)
 jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, long long row_hi,
                        double* __restrict__ o_from, double* __restrict__ o_to,
                        double* __restrict__ o_w, uint8_t* __restrict__ o_u,
-                       unsigned* __restrict__ flags, unsigned tag) {
+                       unsigned* __restrict__ flags, unsigned tag, int lg_group) {
   constexpr bool COUNTS_ONLY = OUT != 0;
   constexpr bool MUT = OUT == 2;
+  constexpr bool GROUPED = OUT == 3;
   using G = SmallK<KP>;
   constexpr int LPE = G::LPE, S = G::S, TS = G::TS, SHIFT = 32 - G::LOG_TS;
   __shared__ unsigned tbl_all[kSmallWarps][TS];
   __shared__ double lut[33];
+  __shared__ __align__(16) uint8_t stage_all[GROUPED ? kSmallWarps : 1][GROUPED ? 512 : 16];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned* tbl = tbl_all[warp];
@@ -256,7 +263,16 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
   __syncthreads();
 
   const long long nwarps = (long long)gridDim.x * kSmallWarps;
-  long long row = row_lo + (long long)blockIdx.x * kSmallWarps + warp;
+  const long long gw = (long long)blockIdx.x * kSmallWarps + warp;
+  // rows of this warp, in the order it visits them: round-robin over the grid (neighbouring warps write
+  // neighbouring output), or -- GROUPED -- round-robin groups of 2^lg_group consecutive rows
+  const int gmask = GROUPED ? (1 << lg_group) - 1 : 0;
+  auto row_of = [&](long long it) -> long long {
+    if (GROUPED) return row_lo + ((gw + (it >> lg_group) * nwarps) << lg_group) + (it & gmask);
+    return row_lo + gw + it * nwarps;
+  };
+  long long it = 0;
+  long long row = row_of(0);
   // which 16-byte piece of a neighbour row this lane fetches
   const char* lane_base = reinterpret_cast<const char*>(idx + (lane % LPE) * 4);
   // SKIP (chosen by the host when k <= KP-4): a 16-byte piece that holds only pads is never fetched
@@ -266,10 +282,10 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
   unsigned warp_flags = 0;
 
   int a_next = (row < row_hi && lane < KP) ? __ldg(idx + row * KP + lane) : kPadId;
-  for (; row < row_hi; row += nwarps) {
+  for (; row < row_hi; row = row_of(++it)) {
     const int a = a_next;  // N(i)[lane], 0-based
     {
-      const long long nrow = row + nwarps;
+      const long long nrow = row_of(it + 1);
       a_next = (nrow < row_hi && lane < KP) ? __ldg(idx + nrow * KP + lane) : kPadId;
     }
     // ---- gather addresses first: the loads do not depend on the hash table
@@ -360,7 +376,22 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     __syncwarp();
     if (valid) tbl[slot] = kEmpty;  // leave the table empty for the next row
     // ---- epilogue: lane e writes edge (i, e)
-    if (valid) {
+    if (GROUPED) {
+      uint8_t* stage = stage_all[warp];
+      const int gr = (int)(it & gmask);  // position of this row inside its group
+      if (valid) stage[gr * k + lane] = (uint8_t)(u | tag);
+      if (gr == gmask || row + 1 >= row_hi) {  // the group is complete (or cut by the end of the range)
+        __syncwarp();
+        const int nbytes = (gr + 1) * k;
+        uint8_t* dst = o_u + (row - gr - row_lo) * (long long)k;
+        if ((nbytes & 15) == 0 && ((unsigned long long)dst & 15ull) == 0) {
+          if (lane < (nbytes >> 4)) reinterpret_cast<uint4*>(dst)[lane] = reinterpret_cast<const uint4*>(stage)[lane];
+        } else {
+          for (int x = lane; x < nbytes; x += 32) dst[x] = stage[x];
+        }
+        __syncwarp();
+      }
+    } else if (valid) {
       const long long r = (row - row_lo) * (long long)k + lane;
       if (COUNTS_ONLY) {
         o_u[r] = (uint8_t)(u | tag);  // tag: the epoch bit of the streaming peer gather (else 0)
@@ -818,7 +849,9 @@ __device__ __forceinline__ unsigned ld_volatile_u8(const uint8_t* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(kExpandThreads)
+constexpr int kStreamBatch = 4;  // edges per thread whose loads are in flight together
+
+__global__ void __launch_bounds__(kExpandThreads, 5)
 expand_stream_kernel(const int* __restrict__ idx, int k, int kp, StreamSegs segs, const uint8_t* d_u,
                      double* __restrict__ o_from, double* __restrict__ o_to, double* __restrict__ o_w,
                      unsigned tag, long long spin_clocks, unsigned* flags) {
@@ -832,33 +865,52 @@ expand_stream_kernel(const int* __restrict__ idx, int k, int kp, StreamSegs segs
   const long long g0 = segs.lo[blockIdx.y] * k + (long long)blockIdx.x * kExpandThreads + threadIdx.x;
   long long row = g0 / k;  // absolute row: d_u, o_* are indexed by absolute edge number
   int j = (int)(g0 % k);
-#pragma unroll 2
-  for (long long e = g0; e < e_hi; e += stride) {
-    const int t = __ldg(idx + row * (long long)kp + j);  // independent of the count byte: issued first
-    unsigned b = ld_volatile_u8(d_u + e);
-    if ((b & 0x80u) != tag) {
-      const long long t0 = clock64();
-      unsigned ns = 64;
-      do {
-        __nanosleep(ns);
-        if (ns < 2048) ns <<= 1;
-        b = ld_volatile_u8(d_u + e);
-        if ((b & 0x80u) != tag && clock64() - t0 > spin_clocks) {
-          atomicOr(flags, kFlagPeerTimeout);
-          return;
-        }
-      } while ((b & 0x80u) != tag);
+  // A thread walks its edges with a grid-wide stride, kStreamBatch of them per round: the id loads
+  // and the (volatile) count-byte loads of a round are all issued before the first byte is looked
+  // at.  One edge per round would make every thread pay a full L2/DRAM round trip per edge, and a
+  // thread that trails the producers by less than that could never keep their pace.
+  for (long long e = g0; e < e_hi; e += kStreamBatch * stride) {
+    long long rows[kStreamBatch];
+    int t[kStreamBatch];
+    unsigned b[kStreamBatch];
+#pragma unroll
+    for (int q = 0; q < kStreamBatch; ++q) {
+      rows[q] = row;
+      const long long eq = e + q * stride;
+      if (eq < e_hi) {
+        t[q] = __ldg(idx + row * (long long)kp + j);  // independent of the count byte
+        b[q] = ld_volatile_u8(d_u + eq);
+      }
+      row += d_row;
+      j += d_j;
+      if (j >= k) {
+        j -= k;
+        ++row;
+      }
     }
-    const int u = (int)(b & 0x7Fu);
-    const bool nz = u > 0;
-    __stcs(o_from + e, nz ? (double)(row + 1) : 0.0);
-    __stcs(o_to + e, nz ? (double)(t + 1) : 0.0);
-    __stcs(o_w + e, lut[u]);
-    row += d_row;
-    j += d_j;
-    if (j >= k) {
-      j -= k;
-      ++row;
+#pragma unroll
+    for (int q = 0; q < kStreamBatch; ++q) {
+      const long long eq = e + q * stride;
+      if (eq >= e_hi) break;
+      unsigned bq = b[q];
+      if ((bq & 0x80u) != tag) {
+        const long long t0 = clock64();
+        unsigned ns = 32;
+        do {
+          __nanosleep(ns);
+          if (ns < 1024) ns <<= 1;
+          bq = ld_volatile_u8(d_u + eq);
+          if ((bq & 0x80u) != tag && clock64() - t0 > spin_clocks) {
+            atomicOr(flags, kFlagPeerTimeout);
+            return;
+          }
+        } while ((bq & 0x80u) != tag);
+      }
+      const int u = (int)(bq & 0x7Fu);
+      const bool nz = u > 0;
+      __stcs(o_from + eq, nz ? (double)(rows[q] + 1) : 0.0);
+      __stcs(o_to + eq, nz ? (double)(t[q] + 1) : 0.0);
+      __stcs(o_w + eq, lut[u]);
     }
   }
 }

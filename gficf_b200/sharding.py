@@ -16,6 +16,7 @@ CPU (tests: partition / assembly logic, with a stand-in compute function) and ``
 """
 from __future__ import annotations
 
+import os
 from typing import Callable
 
 import torch
@@ -162,14 +163,18 @@ def rcpp_parallel_jaccard_coef_sharded(mat, n: int, k: int, out=None, group=None
 # are counted, so that the host rank's expansion of chunk c overlaps everybody's counting of
 # chunk c+1.
 # ---------------------------------------------------------------------------------------------
-def share_bounds(n: int, world: int, host_share: float, host_rank: int = 0):
+def share_bounds(n: int, world: int, host_share: float, host_rank: int = 0, align: int = 1):
     """Contiguous row ranges in rank order: the host rank takes round(host_share * n) rows, the
-    other ranks equal parts of the rest (the last of them takes the remainder)."""
+    other ranks equal parts of the rest (the last of them takes the remainder).  Every boundary
+    except n itself is a multiple of `align` (the streaming peer gather sends groups of up to 16
+    consecutive rows with 16-byte vector stores: its ranges start on multiples of 16 rows)."""
     if world == 1:
         return [(0, n)]
     rows0 = int(round(min(1.0, max(0.0, host_share)) * n))
+    rows0 = min(n, (rows0 + align - 1) // align * align)
     rest = n - rows0
     per = (rest + world - 2) // (world - 1)
+    per = (per + align - 1) // align * align
     sizes, left = [], rest
     for r in range(world):
         if r == host_rank:
@@ -312,12 +317,16 @@ class PeerGather:
             host_share = balanced_host_share(self.world, 1.0, 1.0 if rho is not None else 0.85,
                                              rho if rho is not None else 0.2)
         self.host_share = host_share
-        self.bounds = share_bounds(n, self.world, host_share, host_rank)
+        self.bounds = share_bounds(n, self.world, host_share, host_rank, align=16)
         self.timeout_ms = timeout_ms
         self.epoch = 0
         self.launches = 0
+        # "stream": the host rank's expand polls the bytes while the peers count (default);
+        # "wait": it first waits for a completion flag per peer (A/B switch for measurements)
+        self.mode = os.environ.get("GFICF_PEER_MODE", "stream")
+        self.trace = None  # set to [] to collect (start, mid, end) CUDA events of every host-rank step
         e = n * k
-        self.flag_off = (e + 255) // 256 * 256          # the ack flag lives behind the counts
+        self.flag_off = (e + 255) // 256 * 256          # the ack flag (+ one done flag per rank) lives behind the counts
         nbytes = self.flag_off + 256
         box = [None]
         ok, self.base = 1, 0
@@ -369,15 +378,29 @@ class PeerGather:
             if hi > lo:
                 D.jaccard_counts_tagged_to(idx_full, n, k, lo, hi, self.base + lo * k, tag, self.flags)
                 self.launches += 1
+            if self.mode == "wait":
+                D.signal(ack + 4 * (1 + self.rank), self.epoch)
             return
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if self.trace is not None else None
+        if ev:
+            ev[0].record()
         if hi > lo:  # own rows: fused kernel straight into the output, while the peers count
             D.jaccard_edges(idx_full, n, k, lo, hi, out=out3[:, lo * k:hi * k], flags=self.flags)
             self.launches += 1
+        if ev:
+            ev[1].record()
         segs = [b for r, b in enumerate(self.bounds) if r != self.host and b[1] > b[0]]
+        if self.mode == "wait":
+            for r in range(self.world):
+                if r != self.host:
+                    D.wait_flag(ack + 4 * (1 + r), self.epoch, self.flags)
         if segs:
             D.expand_stream(idx_full, k, segs, self.base, out3, tag, self.flags, self.timeout_ms)
             self.launches += 1
         D.signal(ack, self.epoch)
+        if ev:
+            ev[2].record()
+            self.trace.append(ev)
 
     def finish(self, idx_full, out3) -> int:
         """Collective, after the last step(): agrees on the flag bits of all ranks.  A peer timeout

@@ -58,6 +58,18 @@ inline void Rprintf(const char* fmt, ...) {
 
 typedef std::ptrdiff_t R_xlen_t;
 
+// SEXP stand-in (used by the drop-in bodies of gficf_b200/rpkg/src that take the matrix as it
+// comes from R, integer or double; not used by the reference sources): a tagged matrix handle.
+struct SEXPREC {
+  int type;         // INTSXP or REALSXP
+  int nrow, ncol;
+  void* data;       // column-major int / double storage, owned by the harness
+};
+typedef SEXPREC* SEXP;
+#define INTSXP 13
+#define REALSXP 14
+inline int TYPEOF(SEXP x) { return x->type; }
+
 namespace Rcpp {
 
 // Rcpp::stop(fmt, ...): raises an R error; here a C++ exception the harness catches.
@@ -115,6 +127,18 @@ class NumericMatrix {
   };
 
   NumericMatrix() : nrow_(0), ncol_(0), p_(nullptr) {}
+  // From an R object: a double matrix is wrapped, an integer one is coerced into a fresh double
+  // copy -- what Rcpp's input_parameter<NumericMatrix> does (reference src/RcppExports.cpp:65).
+  NumericMatrix(SEXP x) : nrow_(x->nrow), ncol_(x->ncol), p_(nullptr) {  // NOLINT: implicit like Rcpp's
+    if (x->type == REALSXP) {
+      p_ = static_cast<double*>(x->data);
+    } else {
+      own_.reset(new std::vector<double>((std::size_t)nrow_ * (std::size_t)ncol_));
+      const int* src = static_cast<const int*>(x->data);
+      for (std::size_t i = 0; i < own_->size(); ++i) (*own_)[i] = (double)src[i];
+      p_ = own_->data();
+    }
+  }
   // Fresh zero-filled matrix (what R's allocMatrix + Rcpp's fill does).
   NumericMatrix(int nrow, int ncol)
       : nrow_(nrow), ncol_(ncol),
@@ -146,6 +170,22 @@ class NumericMatrix {
   int nrow_, ncol_;
   std::shared_ptr<std::vector<double> > own_;  // shared like an R object handle
   double* p_;
+};
+
+// An integer matrix as R holds it (INTSXP): column-major int storage, wrapped without a copy.
+class IntegerMatrix {
+ public:
+  IntegerMatrix(SEXP x) : nrow_(x->nrow), ncol_(x->ncol), p_(static_cast<int*>(x->data)) {  // NOLINT
+    if (x->type != INTSXP) throw exception("not an integer matrix");
+  }
+  int nrow() const { return nrow_; }
+  int ncol() const { return ncol_; }
+  int* begin() { return p_; }
+  const int* begin() const { return p_; }
+
+ private:
+  int nrow_, ncol_;
+  int* p_;
 };
 
 // Distinct values of lhs that occur in rhs (set semantics; order unspecified,

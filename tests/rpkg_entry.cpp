@@ -7,7 +7,7 @@
 #include <cstring>
 #include <string>
 
-Rcpp::NumericMatrix rcpp_parallel_jaccard_coef(Rcpp::NumericMatrix mat, bool printOutput);
+Rcpp::NumericMatrix rcpp_parallel_jaccard_coef(SEXP mat, bool printOutput);
 Rcpp::NumericMatrix jaccard_coeff(Rcpp::NumericMatrix idx, bool printOutput);
 int gficf_cuda_devices(int n);
 int gficf_cuda_visible_devices();
@@ -16,16 +16,19 @@ static std::vector<char> g_sink;
 
 extern "C" {
 
-// which: 0 = rcpp_parallel_jaccard_coef, 1 = jaccard_coeff.  Returns 0, or 1 with the R error text.
-int rpkg_call(int which, const double* idx, int n, int k, double* out, int print_output, char* err,
+// which: 0 = rcpp_parallel_jaccard_coef, 1 = jaccard_coeff, 2 = rcpp_parallel_jaccard_coef on an INTEGER
+// matrix (idx then points at int32 data).  Returns 0, or 1 with the R error text.
+int rpkg_call(int which, const void* idx, int n, int k, double* out, int print_output, char* err,
               int errlen, char* printed, int printedlen) {
   g_sink.clear();
   rshim::printf_sink() = &g_sink;
   int rc = 0;
   try {
-    Rcpp::NumericMatrix mat = Rcpp::NumericMatrix::wrap_external(const_cast<double*>(idx), n, k);
-    Rcpp::NumericMatrix res = which == 0 ? rcpp_parallel_jaccard_coef(mat, print_output != 0)
-                                         : jaccard_coeff(mat, print_output != 0);
+    SEXPREC obj = {which == 2 ? INTSXP : REALSXP, n, k, const_cast<void*>(idx)};
+    Rcpp::NumericMatrix res =
+        which == 1 ? jaccard_coeff(Rcpp::NumericMatrix::wrap_external((double*)const_cast<void*>(idx), n, k),
+                                   print_output != 0)
+                   : rcpp_parallel_jaccard_coef(&obj, print_output != 0);
     std::memcpy(out, res.begin(), sizeof(double) * 3 * (size_t)n * (size_t)k);
   } catch (const std::exception& e) {
     snprintf(err, errlen, "%s", e.what());

@@ -37,7 +37,7 @@ class RPkg:
         self.lib.rpkg_call.restype = C.c_int
 
     def call(self, which, idx, print_output=False):
-        a = np.asfortranarray(idx, dtype=np.float64)
+        a = np.asfortranarray(idx, dtype=np.int32 if which == 2 else np.float64)
         n, k = a.shape
         out = np.empty((n * k, 3), dtype=np.float64, order="F")
         err = C.create_string_buffer(1024)

@@ -37,6 +37,10 @@ def test_rpkg_bodies_match_reference(cuda, oracle):
         ser, text = h.call(1, idx, True)
         assert np.array_equal(ser, oracle.serial(idx))
         assert text == "Running Jaccard Coefficient Estimation...\n"
+        # uwot's INTEGER matrix goes in as it is (the documented default of the drop-in body)
+        par_i, text = h.call(2, idx, True)
+        assert np.array_equal(par_i, oracle.parallel(idx))
+        assert text == "Running Parallell Jaccard Coefficient Estimation...\nDone!!\n"
     bad = random_knn(rng, 100, 5)
     bad[3, 2] = 0
     with pytest.raises(RuntimeError) as e:
