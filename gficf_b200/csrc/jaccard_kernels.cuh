@@ -267,12 +267,13 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
   // rows of this warp, in the order it visits them: round-robin over the grid (neighbouring warps write
   // neighbouring output), or -- GROUPED -- round-robin groups of 2^lg_group consecutive rows
   const int gmask = GROUPED ? (1 << lg_group) - 1 : 0;
-  auto row_of = [&](long long it) -> long long {
-    if (GROUPED) return row_lo + ((gw + (it >> lg_group) * nwarps) << lg_group) + (it & gmask);
-    return row_lo + gw + it * nwarps;
+  int gr = 0;  // GROUPED: position of `row` inside its group
+  long long row = GROUPED ? row_lo + (gw << lg_group) : row_lo + gw;
+  // the row this warp visits after `r` (which sits at position `pos` of its group)
+  auto next_row = [&](long long r, int pos) -> long long {
+    if (GROUPED) return pos != gmask ? r + 1 : r - gmask + (nwarps << lg_group);
+    return r + nwarps;
   };
-  long long it = 0;
-  long long row = row_of(0);
   // which 16-byte piece of a neighbour row this lane fetches
   const char* lane_base = reinterpret_cast<const char*>(idx + (lane % LPE) * 4);
   // SKIP (chosen by the host when k <= KP-4): a 16-byte piece that holds only pads is never fetched
@@ -282,10 +283,10 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
   unsigned warp_flags = 0;
 
   int a_next = (row < row_hi && lane < KP) ? __ldg(idx + row * KP + lane) : kPadId;
-  for (; row < row_hi; row = row_of(++it)) {
+  for (; row < row_hi; row = next_row(row, gr), gr = (gr + 1) & gmask) {
     const int a = a_next;  // N(i)[lane], 0-based
     {
-      const long long nrow = row_of(it + 1);
+      const long long nrow = next_row(row, gr);
       a_next = (nrow < row_hi && lane < KP) ? __ldg(idx + nrow * KP + lane) : kPadId;
     }
     // ---- gather addresses first: the loads do not depend on the hash table
@@ -378,7 +379,6 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     // ---- epilogue: lane e writes edge (i, e)
     if (GROUPED) {
       uint8_t* stage = stage_all[warp];
-      const int gr = (int)(it & gmask);  // position of this row inside its group
       if (valid) stage[gr * k + lane] = (uint8_t)(u | tag);
       if (gr == gmask || row + 1 >= row_hi) {  // the group is complete (or cut by the end of the range)
         __syncwarp();
