@@ -10,14 +10,20 @@ A step is one pass of the hot path over the whole matrix.
 
   value     whole-job edges/s with the padded int32 index resident in HBM on every GPU;
             N=1: one launch of the fused kernel; N>1: rows sharded over the ranks (strong
-            scaling: the 4M cells are fixed), per-rank count kernel, NCCL all-gather of the
-            1-byte counts, expand kernel on the host rank
-  e2e       the same metric through the reference-facing call with HOST buffers (pinned):
-            H2D of the f64 R matrix, layout pre-pass, kernel(s), D2H of the (E x 3) doubles
+            scaling: the 4M cells are fixed), ONE count launch per rank whose epilogue stores the
+            parity-tagged 1-byte counts into the host rank's HBM over NVLink, ONE streaming expand
+            launch on the host rank (gficf_b200.sharding.PeerGather)
+  e2e       the same metric through the reference-facing call with HOST buffers (pinned): the f64
+            R matrix narrowed to int32 on its way to the device, layout pre-pass, count kernel, and
+            the (E x 3) doubles written by host threads from the 1-byte counts and by the copy
+            engine at once (include/gficf_cuda.h, gficf_cuda_last_output); bytes as actually moved
+  parity    rank 0: value path and e2e result against the reference's own sources (oracle/_ref) on
+            head / middle / tail rows; at N>1 the whole matrix against the single-GPU fused kernel
   roofline  the fused/count kernel against MEASURED_PEAKS.json hbm_gbs, algorithmic bytes
-            (4k+28) per edge
-  cpu_baseline  the reference's own sources (oracle/_ref, unmodified, R runtime stubbed) on a
-            bounded row sample with all host threads
+            (4k+28) per edge; traffic = DRAM bytes of one launch, measured by an ncu
+            child process in the same run
+  cpu_baseline / cpu_baseline_nt2  the reference's own sources (oracle/_ref, unmodified, R runtime
+            stubbed) on a bounded row sample with all host threads / with nt = 2 (clustcells default)
 
 `--impl reference` times only that CPU implementation (rank 0).
 """
@@ -560,7 +566,32 @@ def run_ours(a):
             dti, tmi, omi = timed_call(r_i32, out_host, 3)
             e2e["int32_input"] = {"value": E / dti, "ms_per_step": dti * 1e3, "h2d_bytes_per_step": int(omi["h2d_bytes"]),
                                   "d2h_bytes_per_step": int(omi["d2h_bytes"]), "output_mode": omi, "breakdown_ms": tmi}
-            del r_i32, r_host, out_host
+            del r_i32
+            # the step after the path through ITS host-buffer entry (gficf_cuda_snn_lower): kNN matrix in,
+            # the CSC arrays RunModularityClustering's edge loop produces out -- instead of the edge matrix
+            if k <= 127:
+                try:
+                    from gficf_b200 import snn
+
+                    bufs = {"colptr": gficf_b200.pinned_empty((n + 1,), dtype=np.int64),
+                            "row": gficf_b200.pinned_empty((E,), dtype=np.int32),
+                            "weight": gficf_b200.pinned_empty((E,), dtype=np.float64),
+                            "vertex_cell": gficf_b200.pinned_empty((n,), dtype=np.int32)}
+                    snn.snn_graph(r_host, out=bufs)
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        g_ = snn.snn_graph(r_host, out=bufs)
+                    dts = (time.perf_counter() - t0) / 3
+                    tms = gficf_b200.last_timings()
+                    e2e["snn_graph"] = {"ms_per_step": dts * 1e3, "nnz": g_["nnz"], "n_vertices": g_["n_vertices"],
+                                        "d2h_bytes_per_step": int(tms["d2h_bytes"]),
+                                        "breakdown_ms": {kk: round(v, 3) for kk, v in tms.items()},
+                                        "call": "gficf_b200.snn.snn_graph (gficf_cuda_snn_lower, pinned host buffers): "
+                                                "replaces Jaccard D2H + R filter + igraph + triangle scan"}
+                    del bufs, g_
+                except Exception as ex:
+                    e2e["snn_graph"] = {"error": str(ex)[:200]}
+            del r_host, out_host
         else:
             # one process per GPU on SHARED host matrices: every rank moves its own rows over its
             # own PCIe link (gficf_cuda_jaccard_rank); rank 0 owns / fills / checks the matrices

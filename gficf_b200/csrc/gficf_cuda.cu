@@ -103,12 +103,18 @@ int sm_count() {
   return sms;
 }
 
+// k > 32: rows are padded to a multiple of GFICF_WIDE_ROW_INTS ints.  16 (64 bytes): a row never
+// straddles an extra 64-byte DRAM burst; 8 (32 bytes, whole sectors): k = 100 fetches 416 instead of
+// 448 bytes per gathered row (A/B in profiles/r02_wide_k.md).
+#ifndef GFICF_WIDE_ROW_INTS
+#define GFICF_WIDE_ROW_INTS 16
+#endif
 int32_t row_stride(int32_t k) {
   if (k <= 4) return 4;
   if (k <= 8) return 8;
   if (k <= 16) return 16;
   if (k <= 32) return 32;
-  return (k + 15) / 16 * 16;  // 64-byte rows: a row never straddles an extra DRAM burst
+  return (k + GFICF_WIDE_ROW_INTS - 1) / GFICF_WIDE_ROW_INTS * GFICF_WIDE_ROW_INTS;
 }
 
 // Table slots per warp-group.  A multiplier is collision free with probability ~exp(-k^2/2/slots)
@@ -1584,7 +1590,9 @@ int gficf_cuda_jaccard_counts_tagged_dev(const int32_t* d_idx_i32, int64_t n, in
   if (!d_idx_i32 || !d_u || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
   if ((tag & ~0x80u) || k > 127) return GFICF_E_LIMIT;
   // k <= 32: grouped rows, 16-byte vector stores (d_u is typically a peer GPU's memory)
-  const bool ok = k <= 32 ? launch_fast<3>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u,
+  const char* store_env = getenv("GFICF_CUDA_PEER_STORE");  // "bytes": row-by-row byte stores (A/B switch)
+  const bool grouped = k <= 32 && !(store_env && !strcmp(store_env, "bytes"));
+  const bool ok = grouped ? launch_fast<3>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u,
                                            d_flags, (cudaStream_t)stream, tag)
                           : launch_fast<1>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u,
                                            d_flags, (cudaStream_t)stream, tag);

@@ -849,9 +849,15 @@ __device__ __forceinline__ unsigned ld_volatile_u8(const uint8_t* p) {
   return v;
 }
 
-constexpr int kStreamBatch = 4;  // edges per thread whose loads are in flight together
+#ifndef GFICF_STREAM_BATCH
+#define GFICF_STREAM_BATCH 2  // edges per thread whose loads are in flight together
+#endif
+#ifndef GFICF_STREAM_MINB
+#define GFICF_STREAM_MINB 8   // resident CTAs per SM the streaming expand is compiled for
+#endif
+constexpr int kStreamBatch = GFICF_STREAM_BATCH;
 
-__global__ void __launch_bounds__(kExpandThreads, 5)
+__global__ void __launch_bounds__(kExpandThreads, GFICF_STREAM_MINB)
 expand_stream_kernel(const int* __restrict__ idx, int k, int kp, StreamSegs segs, const uint8_t* d_u,
                      double* __restrict__ o_from, double* __restrict__ o_to, double* __restrict__ o_w,
                      unsigned tag, long long spin_clocks, unsigned* flags) {

@@ -285,3 +285,36 @@ def test_weight_division_matches_host_for_all_u(cuda):
         w = out[2].cpu().numpy()
         u = cnt.cpu().numpy().astype(np.int64)
         assert np.array_equal(w, u / (2.0 * k - u))
+
+
+@pytest.mark.parametrize("n,k", [(50_000, 30), (20_003, 15), (9_999, 7), (4_001, 32), (3_000, 100), (2_500, 31), (700, 3)])
+def test_streaming_gather_kernels_on_one_gpu(cuda, n, k):
+    """The two kernels of the multi-GPU peer gather, exercised on ONE device: the count kernel that
+    stores parity-tagged bytes (grouped 16-byte vector stores for k <= 32, row-by-row above) into a
+    buffer, and the streaming expand that polls the parity of every byte -- over several segments
+    with odd boundaries, for both parities, must reproduce the fused kernel bit for bit."""
+    from gficf_b200 import device as D
+
+    idx0 = synth.knn_index(n, k, scramble=True, device="cuda")
+    padded, flags = D.pad_rows(idx0)
+    want, _ = D.jaccard_edges(padded, n, k)
+    buf = torch.zeros(n * k + 64, dtype=torch.uint8, device="cuda")
+    cuts = sorted({0, 16 * (n // 48), 16 * (n // 24) + 5, n // 2, n})  # aligned and unaligned slab starts
+    segs = [(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
+    for epoch in (1, 2, 3):
+        tag = (epoch & 1) << 7
+        for lo, hi in segs:
+            D.jaccard_counts_tagged_to(padded, n, k, lo, hi, buf.data_ptr() + lo * k, tag, flags)
+        torch.cuda.synchronize()
+        assert bool(((buf[: n * k] & 0x80) == tag).all())
+        out = torch.full((3, n * k), -1.0, dtype=torch.float64, device="cuda")
+        D.expand_stream(padded, k, segs, buf.data_ptr(), out, tag, flags, timeout_ms=2000)
+        torch.cuda.synchronize()
+        assert int(flags[0]) == 0
+        assert torch.equal(out, want), (n, k, epoch)
+    # a byte that never arrives: the bounded spin gives up and says so instead of hanging the GPU
+    buf[7 * k + 1] ^= 0x80
+    out = torch.empty((3, n * k), dtype=torch.float64, device="cuda")
+    D.expand_stream(padded, k, segs, buf.data_ptr(), out, (3 & 1) << 7, flags, timeout_ms=50)
+    torch.cuda.synchronize()
+    assert int(flags[0]) & 8
