@@ -28,8 +28,10 @@ from .api import (  # noqa: F401
     set_devices,
 )
 
+from .wmu import rcpp_parallel_WMU_test  # noqa: F401,E402
+
 __all__ = [
     "GficfCudaError", "build", "lib", "library_path", "MODE_PARALLEL", "MODE_SERIAL",
     "jaccard_coeff", "rcpp_parallel_jaccard_coef", "phenograph_edges", "pinned_empty",
-    "set_devices", "last_timings", "last_output",
+    "set_devices", "last_timings", "last_output", "rcpp_parallel_WMU_test",
 ]

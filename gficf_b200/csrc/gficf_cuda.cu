@@ -25,8 +25,10 @@
 #include <vector>
 
 #include "host_expand.h"
+#include "host_stats.h"
 #include "jaccard_kernels.cuh"
 #include "snn_kernels.cuh"
+#include "wmu_kernels.cuh"
 #include "nccl_dyn.h"
 
 namespace {
@@ -148,9 +150,7 @@ void launch_small_t(const int* idx, int k, long long lo, long long hi, double* f
   auto kern = jaccard_small_k_kernel<KP, CO, SKIP>;
   const int block = kSmallWarps * 32;
   const int grid = persistent_grid(kern, block, 0, (hi - lo + kSmallWarps - 1) / kSmallWarps);
-  int lg_group = 0;  // CO == 3: rows per group = 16 / gcd(k, 16), so that a group's bytes are whole 16-byte vectors
-  if (CO == 3)
-    while (((k << lg_group) & 15) != 0) ++lg_group;
+  const int lg_group = CO == 3 ? 3 : 0;  // CO == 3: groups of 8 rows (8k bytes: whole 8- or 16-byte vectors)
   const long long work = CO == 3 ? (((hi - lo) >> lg_group) + 1 + kSmallWarps - 1) / kSmallWarps
                                  : (hi - lo + kSmallWarps - 1) / kSmallWarps;
   const int grid3 = CO == 3 ? persistent_grid(kern, block, 0, work) : grid;
@@ -664,7 +664,7 @@ bool h2d_narrow_enabled() {
 }
 
 size_t h2d_block(DeviceWs& ws, const void* src_v, long long ld_src, void* dst_v, long long rows, int cols,
-                 size_t elem, cudaStream_t st) {
+                 size_t elem, cudaStream_t st, bool ids = true) {
   if (rows <= 0 || cols <= 0) return elem;
   const char* src = (const char*)src_v;
   char* dst = (char*)dst_v;
@@ -672,7 +672,7 @@ size_t h2d_block(DeviceWs& ws, const void* src_v, long long ld_src, void* dst_v,
   // narrowing trades host memory traffic (read 8 + write 4 + DMA read 4 bytes per id instead of a DMA
   // read of 8) for PCIe bytes: a win while ONE link is the bottleneck, a loss when several GPUs'
   // links together outrun the host's memory (measured at 8 ranks: 12.4 ms instead of ~3)
-  if (elem == 8 && !small && h2d_narrow_enabled() && g_active_devices.load() * g_sharers.load() == 1) {
+  if (ids && elem == 8 && !small && h2d_narrow_enabled() && g_active_devices.load() * g_sharers.load() == 1) {
     std::vector<Seg> segs;
     for (int c = 0; c < cols; ++c)
       segs.push_back({(char*)(src + (size_t)c * ld_src * 8), dst + (size_t)c * rows * 4, (size_t)rows * 8, nullptr});
@@ -1858,6 +1858,71 @@ int gficf_cuda_snn_lower(const void* idx_colmajor, int32_t elem_bytes, int64_t n
   double tm[8] = {ms[0], ms[1], ms[2], ms[3],
                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), 0, 22,
                   (double)(n + 1) * 8 + (double)total * 12 + (vertex_cell ? (double)nv * 4 : 0.0)};
+  memcpy(tl_timings, tm, sizeof tm);
+  return GFICF_OK;
+  API_END
+}
+
+// ---------------------------------------------------------------- Mann-Whitney U per gene (next row 4)
+int gficf_cuda_wmu_test(const double* mat_x, const double* mat_y, int64_t n_genes, int64_t n1, int64_t n2,
+                        double* out, char* err, size_t errlen) {
+  API_BEGIN
+  if (err && errlen) err[0] = 0;
+  if (n_genes < 0 || n1 < 0 || n2 < 0) throw Err{GFICF_E_ARG, "negative matrix dimension"};
+  if (n_genes == 0) return GFICF_OK;
+  if (!mat_x || !mat_y || !out) throw Err{GFICF_E_ARG, "null matrix pointer"};
+  if (n1 < 1 || n2 < 1) throw Err{GFICF_E_ARG, "both groups need at least one cell"};
+  if (n1 + n2 >= 0x7fffffffLL) throw Err{GFICF_E_LIMIT, "more than 2^31 cells per gene"};
+  if (visible_devices() < 1) throw Err{GFICF_E_CUDA, "no CUDA device is visible (this path has no CPU fallback)"};
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  const auto t0 = std::chrono::steady_clock::now();
+  DeviceWs& ws = g_ws[0];
+  CU_TRY(cudaSetDevice(0));
+  ws.ensure(0);
+  g_active_devices.store(1);
+  const long long N = n1 + n2;
+  int per_sm = 0;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wmu_rank_kernel, kWmuThreads, 0));
+  const int grid = (int)std::min<long long>(n_genes, (long long)std::max(1, per_sm) * sm_count());
+  // device buffers: X | Y in in_raw; per-CTA sort scratch in scratch (keys) and counts (payload);
+  // z, ratio, single flags in out
+  const size_t bx = (size_t)n_genes * n1 * 8, by = (size_t)n_genes * n2 * 8;
+  ws.in_raw.need(bx + by);
+  ws.scratch.need((size_t)grid * 2 * N * sizeof(unsigned long long));
+  ws.counts.need((size_t)grid * (3 * N + 2) * sizeof(unsigned));
+  ws.out.need((size_t)n_genes * (8 + 8 + 4) + 64);
+  double* d_x = (double*)ws.in_raw.p;
+  double* d_y = (double*)((char*)ws.in_raw.p + bx);
+  double* d_z = (double*)ws.out.p;
+  double* d_ratio = d_z + n_genes;
+  int* d_single = (int*)(d_ratio + n_genes);
+  CU_TRY(cudaEventRecord(ws.ev[0], ws.s_comp));
+  h2d_block(ws, mat_x, n_genes * n1, d_x, n_genes * n1, 1, 8, ws.s_comp, /*ids=*/false);
+  h2d_block(ws, mat_y, n_genes * n2, d_y, n_genes * n2, 1, 8, ws.s_comp, /*ids=*/false);
+  CU_TRY(cudaEventRecord(ws.ev[1], ws.s_comp));
+  wmu_rank_kernel<<<grid, kWmuThreads, 0, ws.s_comp>>>(d_x, d_y, n_genes, n1, n2, (unsigned long long*)ws.scratch.p,
+                                                       (unsigned*)ws.counts.p, d_z, d_single);
+  wmu_means_kernel<<<(int)((n_genes + 127) / 128), 128, 0, ws.s_comp>>>(d_x, d_y, n_genes, n1, n2, d_ratio);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaEventRecord(ws.ev[2], ws.s_comp));
+  std::vector<double> h((size_t)n_genes * 2);
+  std::vector<int> hs((size_t)n_genes);
+  CU_TRY(cudaMemcpyAsync(h.data(), d_z, (size_t)n_genes * 16, cudaMemcpyDeviceToHost, ws.s_comp));
+  CU_TRY(cudaMemcpyAsync(hs.data(), d_single, (size_t)n_genes * 4, cudaMemcpyDeviceToHost, ws.s_comp));
+  CU_TRY(cudaStreamSynchronize(ws.s_comp));
+  // the two transcendental steps, one per gene: getPvalue (mann_whitney.cpp:101-110) and log2 (:100)
+  for (int64_t g = 0; g < n_genes; ++g) {
+    out[g] = hs[(size_t)g] ? 1.0 : gficf_host::wmu_pvalue(h[(size_t)g]);
+    out[n_genes + g] = log2(h[(size_t)(n_genes + g)]);
+  }
+  float ms0 = 0, ms1 = 0;
+  CU_TRY(cudaEventElapsedTime(&ms0, ws.ev[0], ws.ev[1]));
+  CU_TRY(cudaEventElapsedTime(&ms1, ws.ev[1], ws.ev[2]));
+  cudaSetDevice(prev_dev);
+  double tm[8] = {ms0, 0, ms1, 0, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
+                  0, 2, (double)n_genes * 20};
   memcpy(tl_timings, tm, sizeof tm);
   return GFICF_OK;
   API_END

@@ -235,8 +235,8 @@ struct SmallK {
 constexpr int kSmallWarps = GFICF_SMALL_WARPS;
 
 // OUT: 0 = (from,to,w) doubles, 1 = counts, 2 = counts with the mutual-neighbour bit (bit 7),
-//      3 = tagged counts for the streaming peer gather: a warp owns GROUPS of 2^lg_group consecutive
-//          rows (group bytes a multiple of 16) and sends a group with 16-byte vector stores -- the
+//      3 = tagged counts for the streaming peer gather: a warp owns GROUPS of 8 consecutive rows
+//          (lg_group = 3) and sends a group with 16-byte (k even) or 8-byte vector stores -- the
 //          destination is a peer GPU's memory, and NVLink carries a few 128-byte packets per group
 //          instead of one or two 30-byte partial-sector packets per row (measured: 7 peers storing
 //          row by row into one GPU are held to 0.67 ms for a 0.40 ms kernel by the packet rate)
@@ -251,15 +251,14 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
   constexpr bool GROUPED = OUT == 3;
   using G = SmallK<KP>;
   constexpr int LPE = G::LPE, S = G::S, TS = G::TS, SHIFT = 32 - G::LOG_TS;
-  __shared__ unsigned tbl_all[kSmallWarps][TS];
-  __shared__ double lut[33];
-  __shared__ __align__(16) uint8_t stage_all[GROUPED ? kSmallWarps : 1][GROUPED ? 512 : 16];
+  __shared__ __align__(16) unsigned tbl_all[kSmallWarps][TS];
+  __shared__ double lut[COUNTS_ONLY ? 1 : 33];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned* tbl = tbl_all[warp];
 #pragma unroll
   for (int x = lane; x < TS; x += 32) tbl[x] = kEmpty;
-  if ((int)threadIdx.x <= k) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
+  if (!COUNTS_ONLY && (int)threadIdx.x <= k) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
   __syncthreads();
 
   const long long nwarps = (long long)gridDim.x * kSmallWarps;
@@ -268,6 +267,7 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
   // neighbouring output), or -- GROUPED -- round-robin groups of 2^lg_group consecutive rows
   const int gmask = GROUPED ? (1 << lg_group) - 1 : 0;
   int gr = 0;  // GROUPED: position of `row` inside its group
+  unsigned cpk0 = 0, cpk1 = 0;  // GROUPED: the group's count bytes of this lane's edge slot
   long long row = GROUPED ? row_lo + (gw << lg_group) : row_lo + gw;
   // the row this warp visits after `r` (which sits at position `pos` of its group)
   auto next_row = [&](long long r, int pos) -> long long {
@@ -378,18 +378,36 @@ jaccard_small_k_kernel(const int* __restrict__ idx, int k, long long row_lo, lon
     if (valid) tbl[slot] = kEmpty;  // leave the table empty for the next row
     // ---- epilogue: lane e writes edge (i, e)
     if (GROUPED) {
-      uint8_t* stage = stage_all[warp];
-      if (valid) stage[gr * k + lane] = (uint8_t)(u | tag);
+      // the row's byte waits in a register (8 rows per group: two packed words per lane); at the end
+      // of the group the bytes pass through the -- at this point empty -- hash table to be regrouped
+      // into 16-byte (k even) or 8-byte (k odd) vectors: no extra shared memory, which would push the
+      // SM's carve-out up a step and take 36 KB of L1 from the lines in flight
+      const unsigned val = (unsigned)(u | tag) & 0xFFu;
+      if (gr < 4) cpk0 |= val << (8 * gr);
+      else cpk1 |= val << (8 * (gr - 4));
       if (gr == gmask || row + 1 >= row_hi) {  // the group is complete (or cut by the end of the range)
+        __syncwarp();  // every lane has erased its key: the table is empty
+        uint8_t* stage = reinterpret_cast<uint8_t*>(tbl);
+        const int nr = gr + 1;
+        if (valid) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (r < nr) stage[r * k + lane] = (uint8_t)((r < 4 ? cpk0 >> (8 * r) : cpk1 >> (8 * (r - 4))) & 0xFFu);
+        }
         __syncwarp();
-        const int nbytes = (gr + 1) * k;
+        const int nbytes = nr * k;
         uint8_t* dst = o_u + (row - gr - row_lo) * (long long)k;
         if ((nbytes & 15) == 0 && ((unsigned long long)dst & 15ull) == 0) {
           if (lane < (nbytes >> 4)) reinterpret_cast<uint4*>(dst)[lane] = reinterpret_cast<const uint4*>(stage)[lane];
+        } else if ((nbytes & 7) == 0 && ((unsigned long long)dst & 7ull) == 0) {
+          if (lane < (nbytes >> 3)) reinterpret_cast<uint2*>(dst)[lane] = reinterpret_cast<const uint2*>(stage)[lane];
         } else {
           for (int x = lane; x < nbytes; x += 32) dst[x] = stage[x];
         }
         __syncwarp();
+        tbl[lane] = kEmpty;  // 8 rows x k <= 256 bytes were used: 64 words
+        tbl[lane + 32] = kEmpty;
+        cpk0 = cpk1 = 0;
       }
     } else if (valid) {
       const long long r = (row - row_lo) * (long long)k + lane;

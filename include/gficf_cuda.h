@@ -310,6 +310,20 @@ int gficf_cuda_snn_lower(const void* idx_colmajor, int32_t elem_bytes, int64_t n
                          int64_t* colptr, int32_t* row, double* w, int64_t cap, int32_t* vertex_cell,
                          int64_t* n_vertices, int64_t* nnz, char* err, size_t errlen);
 
+/* ---- another step of the package that clustcells()'s labels feed: two-sided
+ * Mann-Whitney U per gene with tie correction and continuity correction, and the log2 fold change.
+ * Replaces the body of rcpp_parallel_WMU_test (src/rcpp_parallel_mann_whitney.cpp:106-127, worker
+ * :12-103; helpers src/mann_whitney.cpp:17-131; caller R/deGenes.R:44-54).
+ * mat_x: n_genes x n1, mat_y: n_genes x n2 doubles, COLUMN-major (R matrices: genes are rows, the cells
+ * of the cluster / of all other clusters are columns); out: n_genes x 2 column-major --
+ * column 0 the p-value, column 1 log2(mean(x+1) / mean(y+1)).  The device sorts every gene's
+ * n1+n2 values (CTA per gene, radix sort) and produces the continuity-corrected z and the mean
+ * ratio in exact integer / correctly-rounded arithmetic; the normal cdf (GSL in the reference,
+ * restated from the published algorithm) and log2 are evaluated on the host, once per gene.
+ * Values must not be NaN (the reference's sort is undefined there). ---- */
+int gficf_cuda_wmu_test(const double* mat_x, const double* mat_y, int64_t n_genes, int64_t n1, int64_t n2,
+                        double* out, char* err, size_t errlen);
+
 /* Launch geometry of the last fast-kernel launch on this thread (for the
  * bench record): grid, block, dynamic smem bytes, kernels launched. */
 int gficf_cuda_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* variant);

@@ -20,6 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "libgficf_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libgficf_ref.so")
+REF_WMU_SO = os.path.join(_HERE, "_ref", "libgficf_ref_wmu.so")
 MODOPT_BIN = os.path.join(_HERE, "_ref", "modopt")
 
 _dp = C.POINTER(C.c_double)
@@ -145,3 +146,63 @@ class Reference:
 
     def hw_threads(self) -> int:
         return int(self.lib.gficf_ref_hw_threads())
+
+
+# ---------------------------------------------------------------------------------------------
+# Mann-Whitney U per gene: matX n_genes x n1, matY n_genes x n2 (Fortran order
+# float64, what R hands over) -> n_genes x 2 (p-value, log2 fold change), Fortran order.
+# ---------------------------------------------------------------------------------------------
+def _as_f64(m) -> np.ndarray:
+    a = np.asarray(m)
+    if a.ndim != 2:
+        raise ValueError("a matrix is required")
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+class WmuOracle:
+    """oracle/wmu_oracle.c: our plain-C restatement of rcpp_parallel_mann_whitney.cpp:27-100."""
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build()
+        self.lib = C.CDLL(ORACLE_SO)
+        self.lib.gficf_oracle_wmu.argtypes = [_dp, _dp, C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int32]
+        self.lib.gficf_oracle_wmu.restype = None
+        self.lib.gsl_cdf_ugaussian_P.argtypes = [C.c_double]
+        self.lib.gsl_cdf_ugaussian_P.restype = C.c_double
+        self.lib.gsl_cdf_ugaussian_Q.argtypes = [C.c_double]
+        self.lib.gsl_cdf_ugaussian_Q.restype = C.c_double
+
+    def wmu(self, mat_x, mat_y, nthreads: int | None = None) -> np.ndarray:
+        x, y = _as_f64(mat_x), _as_f64(mat_y)
+        g = x.shape[0]
+        if y.shape[0] != g:
+            raise ValueError("matX and matY must have the same number of rows (genes)")
+        out = np.empty((g, 2), dtype=np.float64, order="F")
+        self.lib.gficf_oracle_wmu(_ptr(x), _ptr(y), g, x.shape[1], y.shape[1], _ptr(out),
+                                  nthreads or os.cpu_count() or 1)
+        return out
+
+
+class WmuReference:
+    """The reference's own mann_whitney.cpp + rcpp_parallel_mann_whitney.cpp (oracle/_ref), R runtime
+    stubbed, GSL's normal cdf restated (parity unpinned on the cdf)."""
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_WMU_SO)
+
+    def __init__(self):
+        if not os.path.exists(REF_WMU_SO):
+            raise FileNotFoundError(REF_WMU_SO + " (build it in the container: make -C oracle ref)")
+        self.lib = C.CDLL(REF_WMU_SO)
+        self.lib.gficf_ref_wmu.argtypes = [_dp, _dp, C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int32, C.c_int32]
+        self.lib.gficf_ref_wmu.restype = C.c_double
+        self.last_seconds = 0.0
+
+    def wmu(self, mat_x, mat_y, nthreads: int = 0) -> np.ndarray:
+        x, y = _as_f64(mat_x), _as_f64(mat_y)
+        g = x.shape[0]
+        out = np.empty((g, 2), dtype=np.float64, order="F")
+        self.last_seconds = self.lib.gficf_ref_wmu(_ptr(x), _ptr(y), g, x.shape[1], y.shape[1], _ptr(out), 0, nthreads)
+        return out

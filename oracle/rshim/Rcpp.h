@@ -22,7 +22,10 @@
 #define GFICF_ORACLE_RSHIM_RCPP_H
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
+#include <functional>
+#include <numeric>
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
@@ -92,6 +95,8 @@ static const Placeholder _ = Placeholder();
 
 class NumericVector {
  public:
+  typedef std::vector<double>::iterator iterator;
+  typedef std::vector<double>::const_iterator const_iterator;
   NumericVector() {}
   explicit NumericVector(std::size_t len) : v_(len, 0.0) {}
   template <typename It>
@@ -100,8 +105,12 @@ class NumericVector {
   std::size_t length() const { return v_.size(); }
   double& operator[](std::size_t i) { return v_[i]; }
   const double& operator[](std::size_t i) const { return v_[i]; }
-  std::vector<double>::const_iterator begin() const { return v_.begin(); }
-  std::vector<double>::const_iterator end() const { return v_.end(); }
+  double& operator()(std::size_t i) { return v_[i]; }  // mann_whitney.cpp:117 res(k)
+  const double& operator()(std::size_t i) const { return v_[i]; }
+  iterator begin() { return v_.begin(); }
+  iterator end() { return v_.end(); }
+  const_iterator begin() const { return v_.begin(); }
+  const_iterator end() const { return v_.end(); }
   void push_back(double x) { v_.push_back(x); }
 
  private:

@@ -16,7 +16,8 @@ def build():
 
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     src = [os.path.join(ROOT, "gficf_b200", "rpkg", "src", f) for f in
-           ("rcpp_parallel_jaccard_coeff.cpp", "jaccard_coeff.cpp", "gficf_cuda_devices.cpp")]
+           ("rcpp_parallel_jaccard_coeff.cpp", "jaccard_coeff.cpp", "gficf_cuda_devices.cpp",
+            "rcpp_parallel_mann_whitney.cpp")]
     lib = gficf_b200.library_path()
     cmd = ["g++", "-O2", "-std=c++11", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "oracle", "rshim"),
            "-I" + os.path.join(ROOT, "include"), os.path.join(HERE, "rpkg_entry.cpp"), *src, lib,
@@ -44,6 +45,23 @@ class RPkg:
         printed = C.create_string_buffer(1024)
         rc = self.lib.rpkg_call(which, a.ctypes.data, n, k, out.ctypes.data, int(print_output), err, 1024,
                                 printed, 1024)
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        return out, printed.value.decode()
+
+    def wmu(self, x, y, print_output=False):
+        x = np.asfortranarray(x, dtype=np.float64)
+        y = np.asfortranarray(y, dtype=np.float64)
+        g = x.shape[0]
+        out = np.empty((g, 2), dtype=np.float64, order="F")
+        err = C.create_string_buffer(1024)
+        printed = C.create_string_buffer(1024)
+        fn = self.lib.rpkg_wmu
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_int,
+                       C.c_char_p, C.c_int]
+        fn.restype = C.c_int
+        rc = fn(x.ctypes.data, y.ctypes.data, g, x.shape[1], y.shape[1], out.ctypes.data, int(print_output), err, 1024,
+                printed, 1024)
         if rc != 0:
             raise RuntimeError(err.value.decode())
         return out, printed.value.decode()

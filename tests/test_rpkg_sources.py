@@ -41,6 +41,15 @@ def test_rpkg_bodies_match_reference(cuda, oracle):
         par_i, text = h.call(2, idx, True)
         assert np.array_equal(par_i, oracle.parallel(idx))
         assert text == "Running Parallell Jaccard Coefficient Estimation...\nDone!!\n"
+    # the Mann-Whitney export of the package, same harness
+    from oracle.binding import WmuOracle
+    from tests.test_wmu_oracle import sc_matrix
+
+    m = sc_matrix(rng, 40, 300)
+    x, y = np.asfortranarray(m[:, :60]), np.asfortranarray(m[:, 60:])
+    res, text = h.wmu(x, y, True)
+    assert np.array_equal(res, WmuOracle().wmu(x, y), equal_nan=True)
+    assert text == "Running Parallell WM-U test...\nDone!!\n"
     bad = random_knn(rng, 100, 5)
     bad[3, 2] = 0
     with pytest.raises(RuntimeError) as e:
@@ -66,7 +75,7 @@ def test_makevars_recipe_builds(tmp_path):
     assert "gficf_cuda.cu" in staged and "snn_kernels.cuh" in staged and "gficf_cuda.h" in staged
     (src / "rshlib.mk").write_text(
         "include Makevars\n"
-        "OBJS = rcpp_parallel_jaccard_coeff.o jaccard_coeff.o gficf_cuda_devices.o\n"
+        "OBJS = rcpp_parallel_jaccard_coeff.o jaccard_coeff.o gficf_cuda_devices.o rcpp_parallel_mann_whitney.o\n"
         "%.o: %.cpp\n\tg++ -std=c++11 -fPIC -O2 -I$(RSHIM) $(PKG_CPPFLAGS) -c $< -o $@\n"
         "$(SHLIB): $(OBJS)\n\tg++ -shared -o $@ $(OBJS) $(PKG_LIBS)\n")
     r = subprocess.run(["make", "-f", "rshlib.mk", "SHLIB=gficf.so", "RSHIM=" + os.path.join(root, "oracle", "rshim"),
@@ -77,4 +86,4 @@ def test_makevars_recipe_builds(tmp_path):
     assert so.gficf_cuda_device_count() >= 0          # the C ABI is inside the package's shared object
     assert b"sm_100a" in ctypes.cast(so.gficf_cuda_version, ctypes.CFUNCTYPE(ctypes.c_char_p))()
     sym = subprocess.run(["nm", "-D", "--defined-only", str(src / "gficf.so")], capture_output=True, text=True).stdout
-    assert "rcpp_parallel_jaccard_coef" in sym and "jaccard_coeff" in sym
+    assert "rcpp_parallel_jaccard_coef" in sym and "jaccard_coeff" in sym and "rcpp_parallel_WMU_test" in sym

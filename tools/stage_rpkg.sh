@@ -8,7 +8,7 @@ ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 DST="${1:?usage: stage_rpkg.sh <package dir>}"
 mkdir -p "$DST/src/cuda" "$DST/tests/testthat"
 cp "$ROOT"/gficf_b200/rpkg/src/*.cpp "$DST/src/"
-cp "$ROOT"/gficf_b200/csrc/gficf_cuda.cu "$ROOT"/gficf_b200/csrc/host_expand.cpp "$ROOT"/gficf_b200/csrc/*.cuh \
+cp "$ROOT"/gficf_b200/csrc/gficf_cuda.cu "$ROOT"/gficf_b200/csrc/host_expand.cpp "$ROOT"/gficf_b200/csrc/host_stats.cpp "$ROOT"/gficf_b200/csrc/*.cuh \
    "$ROOT"/gficf_b200/csrc/*.h "$ROOT"/include/gficf_cuda.h "$DST/src/cuda/"
 touch "$DST/src/Makevars"
 grep -q "cuda/gficf_cuda.o" "$DST/src/Makevars" || cat "$ROOT/gficf_b200/rpkg/src/Makevars.cuda" >> "$DST/src/Makevars"

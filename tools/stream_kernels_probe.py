@@ -19,6 +19,18 @@ for epoch in (1, 2):
     D.expand_stream(padded, k, segs, buf.data_ptr(), out, tag, flags, timeout_ms=2000)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
+def ms(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+lo, hi = segs[3]
+scr = torch.empty((hi - lo) * k, dtype=torch.uint8, device="cuda")
+print("count kernel over 1/7 of the rows: tagged+grouped <3> %.3f ms, plain <1> %.3f ms" % (
+    ms(lambda: D.jaccard_counts_tagged_to(padded, n, k, lo, hi, buf.data_ptr() + lo * k, 0x80, flags)),
+    ms(lambda: D.jaccard_counts(padded, n, k, lo, hi, out=scr, flags=flags))))
 want, _ = D.jaccard_edges(padded, n, k)
 assert torch.equal(out, want) and int(flags[0]) == 0
 print("STREAM_PROBE_OK")
