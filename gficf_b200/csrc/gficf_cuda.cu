@@ -394,7 +394,8 @@ struct DeviceWs {
   // in_raw: device copy of the caller's rows (f64 or int32, column-major); small: flags + n_written
   Buf in_raw, idx, out, counts, scratch, small;
   PinBuf ring, h_counts;  // h_counts: the slab's 1-byte counts on the host (counts-over-PCIe output mode)
-  cudaEvent_t ev_cnt_done = nullptr, ev_exp = nullptr, ev_dma[4] = {};
+  cudaEvent_t ev_cnt_done = nullptr, ev_exp = nullptr, ev_dma[4] = {}, ev_ring = nullptr;
+  bool ring_used = false;  // ev_ring marks the end of the last staged copy through `ring`
   cudaEvent_t ev_slot[kStageSlots] = {};
   unsigned* h_small = nullptr;  // pinned mirror of `small`
 
@@ -412,6 +413,8 @@ struct DeviceWs {
     for (auto& e : ev_dma) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&ev_cnt_done, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&ev_exp, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ev_ring, cudaEventDisableTiming));
+    ring_used = false;
     small.need(64);
     CU_TRY(cudaHostAlloc((void**)&h_small, 64, cudaHostAllocDefault));
     init = true;
@@ -425,6 +428,7 @@ struct DeviceWs {
     h_counts.drop();
     cudaEventDestroy(ev_cnt_done);
     cudaEventDestroy(ev_exp);
+    cudaEventDestroy(ev_ring);
     for (auto& e : ev_dma) cudaEventDestroy(e);
     if (h_small) cudaFreeHost(h_small);
     h_small = nullptr;
@@ -576,6 +580,9 @@ void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cud
   }
   const int np = (int)pieces.size();
   if (!np) return;
+  // the ring may still be the source / target of DMAs queued by the previous staged copy of this
+  // device (two matrices uploaded back to back): wait until those have drained
+  if (ws.ring_used) CU_TRY(cudaEventSynchronize(ws.ev_ring));
   ws.ring.need(kStageChunk * kStageSlots);
   char* ring = (char*)ws.ring.p;
   std::vector<std::atomic<int>> host_done(np), dma_issued(np);
@@ -649,6 +656,7 @@ void staged_copy(DeviceWs& ws, const std::vector<Seg>& segs, bool to_device, cud
     }
   }
   for (auto& t : pool) t.join();
+  if (err == cudaSuccess && cudaEventRecord(ws.ev_ring, st) == cudaSuccess) ws.ring_used = true;
   if (err != cudaSuccess || failed.load())
     throw Err{GFICF_E_CUDA, fmt("staged host copy failed: %s", cudaGetErrorString(err))};
 }
@@ -1588,10 +1596,11 @@ int gficf_cuda_jaccard_counts_tagged_dev(const int32_t* d_idx_i32, int64_t n, in
                                          void* stream) {
   DEV_BEGIN
   if (!d_idx_i32 || !d_u || !d_flags || k < 1 || row_lo < 0 || row_hi > n) return GFICF_E_ARG;
-  if ((tag & ~0x80u) || k > 127) return GFICF_E_LIMIT;
+  if ((tag & ~0x180u) || k > 127) return GFICF_E_LIMIT;
+  const bool by_rows = (tag & 0x100u) != 0;  // GFICF_TAG_ROW_STORES
+  tag &= 0x80u;
   // k <= 32: grouped rows, 16-byte vector stores (d_u is typically a peer GPU's memory)
-  const char* store_env = getenv("GFICF_CUDA_PEER_STORE");  // "bytes": row-by-row byte stores (A/B switch)
-  const bool grouped = k <= 32 && !(store_env && !strcmp(store_env, "bytes"));
+  const bool grouped = k <= 32 && !by_rows;
   const bool ok = grouped ? launch_fast<3>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u,
                                            d_flags, (cudaStream_t)stream, tag)
                           : launch_fast<1>(d_idx_i32, k, row_lo, row_hi, nullptr, nullptr, nullptr, (void*)d_u,

@@ -324,6 +324,11 @@ class PeerGather:
         # "stream": the host rank's expand polls the bytes while the peers count (default);
         # "wait": it first waits for a completion flag per peer (A/B switch for measurements)
         self.mode = os.environ.get("GFICF_PEER_MODE", "stream")
+        # how a peer's count kernel stores into the host rank's memory: groups of 8 rows as 16-byte
+        # vectors (needed from ~6 ranks on: row-by-row stores of 7 peers saturate the host rank's NVLink
+        # packet rate, 0.68 instead of 0.47 ms) or row by row (the faster kernel; measured better at 2 and 4)
+        st = os.environ.get("GFICF_CUDA_PEER_STORE", "auto")
+        self.row_stores = st == "bytes" or (st == "auto" and self.world < 6)
         self.trace = None  # set to [] to collect (start, mid, end) CUDA events of every host-rank step
         e = n * k
         self.flag_off = (e + 255) // 256 * 256          # the ack flag (+ one done flag per rank) lives behind the counts
@@ -376,7 +381,8 @@ class PeerGather:
             # the host rank must have expanded the previous step's counts before they are overwritten
             D.wait_flag(ack, self.epoch - 1, self.flags)
             if hi > lo:
-                D.jaccard_counts_tagged_to(idx_full, n, k, lo, hi, self.base + lo * k, tag, self.flags)
+                D.jaccard_counts_tagged_to(idx_full, n, k, lo, hi, self.base + lo * k,
+                                           tag | (0x100 if self.row_stores else 0), self.flags)
                 self.launches += 1
             if self.mode == "wait":
                 D.signal(ack + 4 * (1 + self.rank), self.epoch)

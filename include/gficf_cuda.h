@@ -189,7 +189,13 @@ int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_
  * default of gficf_b200.sharding.PeerGather).  Every count byte carries the step's parity in bit 7
  * (`tag` = 0x00 / 0x80, alternating from step to step; k <= 127), so a byte is its own ready flag:
  *   gficf_cuda_jaccard_counts_tagged_dev   the count kernel of gficf_cuda_jaccard_counts_dev, storing
- *                                          u | tag (d_u: typically the host rank's mapped buffer)
+ *                                          u | tag (d_u: typically the host rank's mapped buffer).  For
+ *                                          k <= 32 a warp owns groups of 8 consecutive rows and sends a
+ *                                          group with 16-byte vector stores (few full NVLink packets
+ *                                          instead of one or two <= 30-byte packets per row: what keeps
+ *                                          7 peers from saturating one GPU's ingress packet rate);
+ *                                          tag | GFICF_TAG_ROW_STORES keeps row-by-row byte stores (the
+ *                                          faster kernel by ~15 %: the better choice up to ~4 peers)
  *   gficf_cuda_expand_stream_dev           host rank: expands the rows of n_seg row segments (one per
  *                                          contributing rank; seg_lo/seg_hi are HOST arrays of absolute
  *                                          rows) while the peers are still storing into d_u, polling each
@@ -197,6 +203,7 @@ int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_
  *                                          indexed by ABSOLUTE edge number i*k+j.  timeout_ms bounds
  *                                          every spin (0: GFICF_CUDA_PEER_TIMEOUT_MS, default 20000);
  *                                          GFICF_FLAG_PEER_TIMEOUT in *d_flags means the output is invalid. */
+#define GFICF_TAG_ROW_STORES 0x100u
 int gficf_cuda_jaccard_counts_tagged_dev(const int32_t* d_idx_i32, int64_t n, int32_t k, int64_t row_lo,
                                          int64_t row_hi, uint8_t* d_u, uint32_t tag, uint32_t* d_flags,
                                          void* stream);

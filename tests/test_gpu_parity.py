@@ -301,10 +301,11 @@ def test_streaming_gather_kernels_on_one_gpu(cuda, n, k):
     buf = torch.zeros(n * k + 64, dtype=torch.uint8, device="cuda")
     cuts = sorted({0, 16 * (n // 48), 16 * (n // 24) + 5, n // 2, n})  # aligned and unaligned slab starts
     segs = [(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
-    for epoch in (1, 2, 3):
+    for epoch in (1, 2, 3, 4):
         tag = (epoch & 1) << 7
-        for lo, hi in segs:
-            D.jaccard_counts_tagged_to(padded, n, k, lo, hi, buf.data_ptr() + lo * k, tag, flags)
+        for lo, hi in segs:  # epochs 3, 4: row-by-row byte stores (GFICF_TAG_ROW_STORES)
+            D.jaccard_counts_tagged_to(padded, n, k, lo, hi, buf.data_ptr() + lo * k, tag | (0x100 if epoch > 2 else 0),
+                                       flags)
         torch.cuda.synchronize()
         assert bool(((buf[: n * k] & 0x80) == tag).all())
         out = torch.full((3, n * k), -1.0, dtype=torch.float64, device="cuda")
@@ -315,6 +316,6 @@ def test_streaming_gather_kernels_on_one_gpu(cuda, n, k):
     # a byte that never arrives: the bounded spin gives up and says so instead of hanging the GPU
     buf[7 * k + 1] ^= 0x80
     out = torch.empty((3, n * k), dtype=torch.float64, device="cuda")
-    D.expand_stream(padded, k, segs, buf.data_ptr(), out, (3 & 1) << 7, flags, timeout_ms=50)
+    D.expand_stream(padded, k, segs, buf.data_ptr(), out, (4 & 1) << 7, flags, timeout_ms=50)
     torch.cuda.synchronize()
     assert int(flags[0]) & 8

@@ -56,6 +56,18 @@ def test_wmu_large_n_ordered_tie_sum(cuda):
     _check(cuda, np.asfortranarray(m[:, :n1]), np.asfortranarray(m[:, n1:]))
 
 
+def test_wmu_many_genes_per_cta_and_staged_uploads(cuda):
+    """More genes than resident CTAs (a CTA sorts several genes in turn) and matrices above the
+    8 MiB small-copy threshold (both go through the pinned staging ring, back to back)."""
+    rng = np.random.default_rng(11)
+    genes, n1, n2 = 2500, 300, 2200   # 6 MB + 44 MB of pageable doubles
+    m = sc_matrix(rng, genes, n1 + n2)
+    _check(cuda, np.asfortranarray(m[:, :n1]), np.asfortranarray(m[:, n1:]))
+    genes, n1, n2 = 120, 12_000, 30_000  # both above 8 MiB
+    m = sc_matrix(rng, genes, n1 + n2)
+    _check(cuda, np.asfortranarray(m[:, :n1]), np.asfortranarray(m[:, n1:]))
+
+
 def test_wmu_argument_errors(cuda):
     x = np.asfortranarray(np.ones((4, 3)))
     with pytest.raises(ValueError):

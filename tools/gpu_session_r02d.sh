@@ -12,6 +12,6 @@ try:
 except Exception as ex:
     print('$1 failed', ex)
 "; }
-run | show grouped | tee gpurun_out/peer_store_n$N.txt
+GFICF_CUDA_PEER_STORE=grouped run | show grouped | tee gpurun_out/peer_store_n$N.txt
 GFICF_CUDA_PEER_STORE=bytes run | show bytes | tee -a gpurun_out/peer_store_n$N.txt
 GFICF_PEER_MODE=wait run | show grouped-wait | tee -a gpurun_out/peer_store_n$N.txt
