@@ -1913,7 +1913,8 @@ int gficf_cuda_wmu_test(const double* mat_x, const double* mat_y, int64_t n_gene
   CU_TRY(cudaEventRecord(ws.ev[1], ws.s_comp));
   wmu_rank_kernel<<<grid, kWmuThreads, 0, ws.s_comp>>>(d_x, d_y, n_genes, n1, n2, (unsigned long long*)ws.scratch.p,
                                                        (unsigned*)ws.counts.p, d_z, d_single);
-  wmu_means_kernel<<<(int)((n_genes + 127) / 128), 128, 0, ws.s_comp>>>(d_x, d_y, n_genes, n1, n2, d_ratio);
+  wmu_means_kernel<<<(int)((n_genes + kMeanGenes - 1) / kMeanGenes), kMeanThreads, 0, ws.s_comp>>>(d_x, d_y, n_genes, n1, n2,
+                                                                                                   d_ratio);
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaEventRecord(ws.ev[2], ws.s_comp));
   std::vector<double> h((size_t)n_genes * 2);
