@@ -43,8 +43,6 @@ PROTOTYPES = {
     "gficf_cuda_ipc_free": (C.c_int, [_vp]),
     "gficf_cuda_signal_dev": (C.c_int, [_vp, C.c_uint32, _vp]),
     "gficf_cuda_wait_dev": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
-    "gficf_cuda_expand_wait_dev": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp,
-                                             C.c_int32, C.c_uint32, C.c_int64, _vp, _vp]),
     "gficf_cuda_jaccard_counts_tagged_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _vp,
                                                        C.c_uint32, _vp, _vp]),
     "gficf_cuda_expand_stream_dev": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),

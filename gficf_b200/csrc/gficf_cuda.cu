@@ -320,7 +320,7 @@ void launch_expand_t(const int* idx, int k, long long lo, long long hi, const CT
   if (total <= 0) return;
   if (mode == GFICF_MODE_PARALLEL) {
     expand_fixed_kernel<CT><<<grid_1d(total, kExpandThreads, 8), kExpandThreads, 0, st>>>(
-        idx, k, kp, lo, hi, d_u, f, t, w, nullptr, 0, 0u, 0, nullptr, 0);
+        idx, k, kp, lo, hi, d_u, f, t, w);
   } else {
     long long* chunk = (long long*)scratch;
     const long long nchunks = (total + kCompactChunk - 1) / kCompactChunk;
@@ -1511,25 +1511,6 @@ int gficf_cuda_wait_dev(const uint32_t* d_flag, uint32_t expected, uint32_t* d_f
   API_BEGIN
   if (!d_flag || !d_flags) return GFICF_E_ARG;
   wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_flag, expected, d_flags, peer_spin_clocks(0));
-  CU_TRY(cudaGetLastError());
-  return GFICF_OK;
-  API_END
-}
-
-int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, int64_t row_hi,
-                               const uint8_t* d_u, double* d_from, double* d_to, double* d_w,
-                               const uint32_t* d_ready, int32_t n_ready, uint32_t expected,
-                               int64_t chunk_rows, uint32_t* d_flags, void* stream) {
-  char* err = nullptr;
-  size_t errlen = 0;
-  API_BEGIN
-  if (!d_idx_i32 || !d_u || !d_from || !d_to || !d_w || k < 1 || k > 255 || row_lo < 0) return GFICF_E_ARG;
-  if (d_ready && (!d_flags || n_ready < 1 || n_ready > kExpandThreads)) return GFICF_E_ARG;
-  const long long total = (row_hi - row_lo) * (long long)k;
-  if (total <= 0) return GFICF_OK;
-  expand_fixed_kernel<uint8_t><<<grid_1d(total, kExpandThreads, 8), kExpandThreads, 0, (cudaStream_t)stream>>>(
-      d_idx_i32, k, row_stride(k), row_lo, row_hi, d_u, d_from, d_to, d_w, d_ready, n_ready, expected,
-      chunk_rows, d_flags, peer_spin_clocks(0));
   CU_TRY(cudaGetLastError());
   return GFICF_OK;
   API_END

@@ -783,10 +783,6 @@ jaccard_exact_kernel(const int* __restrict__ idx, int k, int kp, long long row_l
 // ---------------------------------------------------------------------------
 // counts -> edge rows, fixed slots (mode 0).  One thread per edge, streaming.
 // ---------------------------------------------------------------------------
-// When `ready` is given, every CTA first waits until ready[0..n_ready) >= expected: the counts of
-// this row range are being stored into this GPU's memory by PEER GPUs' count kernels (NVLink
-// stores), and each peer raises its flag (signal_kernel) once its kernel has finished.  A bounded spin: after
-// spin_clocks the kernel gives up and reports GFICF_FLAG_PEER_TIMEOUT instead of hanging the GPU.
 constexpr unsigned kFlagPeerTimeout = 8u;
 
 constexpr int kExpandThreads = 256;
@@ -795,60 +791,36 @@ template <typename CT>
 __global__ void __launch_bounds__(kExpandThreads)
 expand_fixed_kernel(const int* __restrict__ idx, int k, int kp, long long row_lo, long long row_hi,
                     const CT* d_u, double* __restrict__ o_from, double* __restrict__ o_to,
-                    double* __restrict__ o_w, const volatile unsigned* ready, int n_ready,
-                    unsigned expected, long long chunk_rows, unsigned* flags, long long spin_clocks) {
+                    double* __restrict__ o_w) {
   __shared__ double lut[256];
   const bool use_lut = k <= 255;
   if (use_lut && (int)threadIdx.x <= k) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
-  // Row chunks: chunk c (rows [row_lo + c*chunk_rows, ...)) may be expanded once every flag has
-  // reached expected + c.  chunk_rows <= 0: a single chunk.  With chunks the kernel is launched
-  // ONCE for the whole matrix and streams behind the ranks that are still counting.
-  const long long rows_total = row_hi - row_lo;
-  const long long crow = chunk_rows > 0 ? chunk_rows : rows_total;
+  __syncthreads();
+  // Grid-stride over the edges (at any moment the whole grid writes ONE contiguous window of each
+  // output array: DRAM-page friendly), with a (row, j) walk that needs no division per edge: one
+  // division per thread, then fixed increments.
   const long long stride = (long long)gridDim.x * kExpandThreads;
   const long long d_row = stride / k;
   const int d_j = (int)(stride % k);
-  unsigned chunk = 0;
-  for (long long c_lo = 0; c_lo < rows_total; c_lo += crow, ++chunk) {
-    if (ready != nullptr && (int)threadIdx.x < n_ready) {
-      // thread r waits for rank r's flag
-      const long long t0 = clock64();
-      while ((int)(ready[threadIdx.x] - (expected + chunk)) < 0) {
-        if (clock64() - t0 > spin_clocks) {
-          atomicOr(flags, kFlagPeerTimeout);
-          break;
-        }
-        __nanosleep(200);
-      }
-      __threadfence();
-    }
-    __syncthreads();
-    // Grid-stride over the chunk's edges (at any moment the whole grid writes ONE contiguous
-    // window of each output array: DRAM-page friendly), with a (row, j) walk that needs no
-    // division per edge: one division per thread and chunk, then fixed increments.
-    const long long e_lo = c_lo * k;
-    const long long e_hi = min(rows_total, c_lo + crow) * k;
-    const long long g0 = e_lo + (long long)blockIdx.x * kExpandThreads + threadIdx.x;
-    long long row = row_lo + g0 / k;
-    int j = (int)(g0 % k);
+  const long long e_hi = (row_hi - row_lo) * k;
+  const long long g0 = (long long)blockIdx.x * kExpandThreads + threadIdx.x;
+  long long row = row_lo + g0 / k;
+  int j = (int)(g0 % k);
 #pragma unroll 4
-    for (long long e = g0; e < e_hi; e += stride) {
-      // the counts may have been stored by a peer GPU: read them from L2 (ld.global.cg), the point
-      // of coherence for this GPU's memory, never through the non-coherent path
-      const int u = (int)__ldcg(d_u + e);
-      // the id is loaded unconditionally: a load that waits for u first doubles the latency chain
-      // (measured 0.98 -> 0.62 ms at 4M x 30, tools/expand_bench.cu)
-      const int t = __ldg(idx + row * (long long)kp + j);
-      const bool nz = u > 0;
-      __stcs(o_from + e, nz ? (double)(row + 1) : 0.0);
-      __stcs(o_to + e, nz ? (double)(t + 1) : 0.0);
-      __stcs(o_w + e, use_lut ? lut[u] : (nz ? jaccard_weight(u, k) : 0.0));
-      row += d_row;
-      j += d_j;
-      if (j >= k) {
-        j -= k;
-        ++row;
-      }
+  for (long long e = g0; e < e_hi; e += stride) {
+    const int u = (int)__ldcg(d_u + e);
+    // the id is loaded unconditionally: a load that waits for u first doubles the latency chain
+    // (measured 0.98 -> 0.62 ms at 4M x 30, tools/expand_bench.cu)
+    const int t = __ldg(idx + row * (long long)kp + j);
+    const bool nz = u > 0;
+    __stcs(o_from + e, nz ? (double)(row + 1) : 0.0);
+    __stcs(o_to + e, nz ? (double)(t + 1) : 0.0);
+    __stcs(o_w + e, use_lut ? lut[u] : (nz ? jaccard_weight(u, k) : 0.0));
+    row += d_row;
+    j += d_j;
+    if (j >= k) {
+      j -= k;
+      ++row;
     }
   }
 }
@@ -949,7 +921,8 @@ expand_stream_kernel(const int* __restrict__ idx, int k, int kp, StreamSegs segs
   }
 }
 
-// holds the stream until *flag >= expected (bounded spin, see expand_fixed_kernel)
+// holds the stream until *flag >= expected (bounded spin: after spin_clocks it raises
+// GFICF_FLAG_PEER_TIMEOUT instead of hanging the GPU)
 __global__ void wait_kernel(const volatile unsigned* flag, unsigned expected, unsigned* flags,
                             long long spin_clocks) {
   const long long t0 = clock64();

@@ -182,20 +182,6 @@ def wait_flag(flag_ptr: int, expected: int, flags: torch.Tensor) -> None:
     _lib.check(_lib.lib().gficf_cuda_wait_dev(flag_ptr, expected & 0xFFFFFFFF, flags.data_ptr(), _stream_ptr()))
 
 
-def expand_wait(idx_i32: torch.Tensor, k: int, row_lo: int, row_hi: int, counts_ptr: int, out3: torch.Tensor,
-                ready_ptr: int, n_ready: int, expected: int, flags: torch.Tensor, chunk_rows: int = 0) -> None:
-    """Fixed-slot expand of rows [row_lo,row_hi) from counts at counts_ptr (slab-relative) into
-    out3[:, row_lo*k:row_hi*k], after the n_ready flags at ready_ptr are all >= expected
-    (ready_ptr = 0: no wait).  chunk_rows > 0: one launch that expands chunk c once the flags reach
-    expected + c."""
-    sl = out3[:, row_lo * k:row_hi * k]
-    with torch.cuda.device(idx_i32.device):
-        _lib.check(_lib.lib().gficf_cuda_expand_wait_dev(idx_i32.data_ptr(), k, row_lo, row_hi, counts_ptr,
-                                                         sl[0].data_ptr(), sl[1].data_ptr(), sl[2].data_ptr(),
-                                                         ready_ptr or None, n_ready, expected & 0xFFFFFFFF,
-                                                         int(chunk_rows), flags.data_ptr(), _stream_ptr()))
-
-
 def jaccard_counts_tagged_to(idx_i32: torch.Tensor, n: int, k: int, row_lo: int, row_hi: int, out_ptr: int,
                              tag: int, flags: torch.Tensor) -> None:
     """Count kernel storing u | tag (tag = 0x00 / 0x80: the step parity of the streaming peer gather,

@@ -162,15 +162,12 @@ int gficf_cuda_jaccard_rank(const double* idx_colmajor, int64_t n, int32_t k, do
 
 /* ======================================================================== *
  *  Peer-memory gather (fused compute + gather over NVLink, one process per GPU):
- *  the host rank allocates the count buffer and exports it; the other ranks map
- *  it and pass the mapped pointer as d_u of gficf_cuda_jaccard_counts_dev, so the
- *  count kernel's epilogue stores its 1-byte results straight into the host
- *  rank's HBM.  gficf_cuda_signal_dev raises a flag in that buffer when the
- *  stream reaches it; gficf_cuda_expand_wait_dev is the expand kernel that first
- *  waits until d_ready[0..n_ready) >= expected, one flag per contributing rank
- *  (bounded spin; GFICF_FLAG_PEER_TIMEOUT on give-up).  With chunk_rows > 0 the rows
- *  are expanded chunk by chunk in ONE launch: chunk c waits for the flags to reach
- *  expected + c, so the kernel streams behind ranks that are still counting.
+ *  the host rank allocates the count buffer and exports it (CUDA IPC); the other
+ *  ranks map it and pass the mapped pointer as the output of their count kernel, so
+ *  the kernel's epilogue stores its 1-byte results straight into the host rank's HBM.
+ *  gficf_cuda_signal_dev raises a flag in that buffer when the stream reaches it,
+ *  gficf_cuda_wait_dev holds a stream until a flag reaches a value (bounded spin;
+ *  GFICF_FLAG_PEER_TIMEOUT on give-up): the one ack per step of the protocol below.
  * ======================================================================== */
 #define GFICF_IPC_HANDLE_BYTES 64
 #define GFICF_FLAG_PEER_TIMEOUT 8u
@@ -180,13 +177,9 @@ int gficf_cuda_ipc_close(void* dptr);
 int gficf_cuda_ipc_free(void* dptr);
 int gficf_cuda_signal_dev(uint32_t* d_flag, uint32_t value, void* stream);
 int gficf_cuda_wait_dev(const uint32_t* d_flag, uint32_t expected, uint32_t* d_flags, void* stream);
-int gficf_cuda_expand_wait_dev(const int32_t* d_idx_i32, int32_t k, int64_t row_lo, int64_t row_hi,
-                               const uint8_t* d_u, double* d_from, double* d_to, double* d_w,
-                               const uint32_t* d_ready, int32_t n_ready, uint32_t expected,
-                               int64_t chunk_rows, uint32_t* d_flags, void* stream);
 
-/* Streaming form of the peer-memory gather (no flags, no fences, one launch per rank and step; the
- * default of gficf_b200.sharding.PeerGather).  Every count byte carries the step's parity in bit 7
+/* The gather itself (no data flags, no fences, one launch per rank and step;
+ * gficf_b200.sharding.PeerGather).  Every count byte carries the step's parity in bit 7
  * (`tag` = 0x00 / 0x80, alternating from step to step; k <= 127), so a byte is its own ready flag:
  *   gficf_cuda_jaccard_counts_tagged_dev   the count kernel of gficf_cuda_jaccard_counts_dev, storing
  *                                          u | tag (d_u: typically the host rank's mapped buffer).  For
