@@ -1612,12 +1612,26 @@ int gficf_cuda_expand_stream_dev(const int32_t* d_idx_i32, int32_t k, const int6
   if (!ns) return GFICF_OK;
   // the resident CTAs are shared evenly by the segments: every sub-grid then advances
   // through its segment at the same rate as the ranks that produce the segments
+  // two adjacent edges per thread (16-byte stores) when every output column is 16-byte aligned and every
+  // segment starts on an even edge; GFICF_CUDA_STREAM_WIDTH=1 forces the one-edge form (A/B switch)
+  bool pair = (((uintptr_t)d_from | (uintptr_t)d_to | (uintptr_t)d_w) & 15) == 0 && ((uintptr_t)d_u & 1) == 0;
+  for (int i = 0; i < ns; ++i) pair = pair && ((segs.lo[i] * (long long)k) & 1) == 0;
+  const char* we = getenv("GFICF_CUDA_STREAM_WIDTH");
+  if (we && we[0] == '1') pair = false;
+  const int w = pair ? 2 : 1;
   int per_sm = 0;
-  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_stream_kernel, kExpandThreads, 0));
+  if (pair) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_stream_kernel<2>, kExpandThreads, 0));
+  else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_stream_kernel<1>, kExpandThreads, 0));
   long long gx = std::max<long long>(1, (long long)sm_count() * std::max(1, per_sm) / ns);
-  gx = std::min<long long>(gx, (longest + kExpandThreads - 1) / kExpandThreads);
-  expand_stream_kernel<<<dim3((unsigned)gx, (unsigned)ns), kExpandThreads, 0, (cudaStream_t)stream>>>(
-      d_idx_i32, k, row_stride(k), segs, d_u, d_from, d_to, d_w, tag, peer_spin_clocks(timeout_ms), d_flags);
+  gx = std::min<long long>(gx, (longest / w + kExpandThreads - 1) / kExpandThreads);
+  gx = std::max<long long>(gx, 1);
+  const dim3 grid((unsigned)gx, (unsigned)ns);
+  if (pair)
+    expand_stream_kernel<2><<<grid, kExpandThreads, 0, (cudaStream_t)stream>>>(
+        d_idx_i32, k, row_stride(k), segs, d_u, d_from, d_to, d_w, tag, peer_spin_clocks(timeout_ms), d_flags);
+  else
+    expand_stream_kernel<1><<<grid, kExpandThreads, 0, (cudaStream_t)stream>>>(
+        d_idx_i32, k, row_stride(k), segs, d_u, d_from, d_to, d_w, tag, peer_spin_clocks(timeout_ms), d_flags);
   CU_TRY(cudaGetLastError());
   return GFICF_OK;
   DEV_END

@@ -856,8 +856,29 @@ __device__ __forceinline__ unsigned ld_volatile_u8(const uint8_t* p) {
 #define GFICF_STREAM_MINB 8   // resident CTAs per SM the streaming expand is compiled for
 #endif
 constexpr int kStreamBatch = GFICF_STREAM_BATCH;
+#ifndef GFICF_STREAM_STORE
+#define GFICF_STREAM_STORE 0  // 0: st.global.cs (evict first), 1: default policy
+#endif
 
-__global__ void __launch_bounds__(kExpandThreads, GFICF_STREAM_MINB)
+template <typename V>
+__device__ __forceinline__ void stream_store(V* p, V v) {
+#if GFICF_STREAM_STORE == 0
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
+__device__ __forceinline__ unsigned ld_volatile_u16(const uint8_t* p) {
+  unsigned short v;
+  asm volatile("ld.volatile.global.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+
+// W = edges per thread and round that are adjacent in memory: 1 (8-byte stores) or 2 (one 16-bit
+// count load, 16-byte stores; needs 16-byte aligned output columns and even segment starts)
+template <int W>
+__global__ void __launch_bounds__(kExpandThreads, W == 2 ? 6 : GFICF_STREAM_MINB)
 expand_stream_kernel(const int* __restrict__ idx, int k, int kp, StreamSegs segs, const uint8_t* d_u,
                      double* __restrict__ o_from, double* __restrict__ o_to, double* __restrict__ o_w,
                      unsigned tag, long long spin_clocks, unsigned* flags) {
@@ -865,27 +886,36 @@ expand_stream_kernel(const int* __restrict__ idx, int k, int kp, StreamSegs segs
   if ((int)threadIdx.x <= k && threadIdx.x < 128) lut[threadIdx.x] = jaccard_weight((int)threadIdx.x, k);
   __syncthreads();
   const long long e_hi = segs.hi[blockIdx.y] * k;
-  const long long stride = (long long)gridDim.x * kExpandThreads;
+  const long long stride = (long long)gridDim.x * kExpandThreads * W;
   const long long d_row = stride / k;
   const int d_j = (int)(stride % k);
-  const long long g0 = segs.lo[blockIdx.y] * k + (long long)blockIdx.x * kExpandThreads + threadIdx.x;
+  const long long g0 = segs.lo[blockIdx.y] * k + ((long long)blockIdx.x * kExpandThreads + threadIdx.x) * W;
   long long row = g0 / k;  // absolute row: d_u, o_* are indexed by absolute edge number
   int j = (int)(g0 % k);
-  // A thread walks its edges with a grid-wide stride, kStreamBatch of them per round: the id loads
+  const unsigned want = W == 2 ? tag * 0x0101u : tag, pmask = W == 2 ? 0x8080u : 0x80u;
+  // A thread walks its edges with a grid-wide stride, kStreamBatch items per round: the id loads
   // and the (volatile) count-byte loads of a round are all issued before the first byte is looked
   // at.  One edge per round would make every thread pay a full L2/DRAM round trip per edge, and a
   // thread that trails the producers by less than that could never keep their pace.
   for (long long e = g0; e < e_hi; e += kStreamBatch * stride) {
     long long rows[kStreamBatch];
-    int t[kStreamBatch];
+    int js[kStreamBatch];
+    int t[kStreamBatch][W];
     unsigned b[kStreamBatch];
 #pragma unroll
     for (int q = 0; q < kStreamBatch; ++q) {
       rows[q] = row;
+      js[q] = j;
       const long long eq = e + q * stride;
       if (eq < e_hi) {
-        t[q] = __ldg(idx + row * (long long)kp + j);  // independent of the count byte
-        b[q] = ld_volatile_u8(d_u + eq);
+        t[q][0] = __ldg(idx + row * (long long)kp + j);  // independent of the count byte
+        if (W == 2) {
+          const bool wrap = j + 1 >= k;  // the second edge starts the next row
+          if (eq + 1 < e_hi) t[q][W - 1] = __ldg(idx + (row + (wrap ? 1 : 0)) * (long long)kp + (wrap ? 0 : j + 1));
+          b[q] = eq + 1 < e_hi ? ld_volatile_u16(d_u + eq) : (ld_volatile_u8(d_u + eq) | (want & 0xFF00u));
+        } else {
+          b[q] = ld_volatile_u8(d_u + eq);
+        }
       }
       row += d_row;
       j += d_j;
@@ -899,24 +929,33 @@ expand_stream_kernel(const int* __restrict__ idx, int k, int kp, StreamSegs segs
       const long long eq = e + q * stride;
       if (eq >= e_hi) break;
       unsigned bq = b[q];
-      if ((bq & 0x80u) != tag) {
+      if ((bq & pmask) != want) {
         const long long t0 = clock64();
         unsigned ns = 32;
         do {
           __nanosleep(ns);
           if (ns < 1024) ns <<= 1;
-          bq = ld_volatile_u8(d_u + eq);
-          if ((bq & 0x80u) != tag && clock64() - t0 > spin_clocks) {
+          bq = (W == 2 && eq + 1 < e_hi) ? ld_volatile_u16(d_u + eq)
+                                         : (ld_volatile_u8(d_u + eq) | (W == 2 ? (want & 0xFF00u) : 0u));
+          if ((bq & pmask) != want && clock64() - t0 > spin_clocks) {
             atomicOr(flags, kFlagPeerTimeout);
             return;
           }
-        } while ((bq & 0x80u) != tag);
+        } while ((bq & pmask) != want);
       }
-      const int u = (int)(bq & 0x7Fu);
-      const bool nz = u > 0;
-      __stcs(o_from + eq, nz ? (double)(rows[q] + 1) : 0.0);
-      __stcs(o_to + eq, nz ? (double)(t[q] + 1) : 0.0);
-      __stcs(o_w + eq, lut[u]);
+      const int u0 = (int)(bq & 0x7Fu);
+      const double f0 = u0 > 0 ? (double)(rows[q] + 1) : 0.0, t0v = u0 > 0 ? (double)(t[q][0] + 1) : 0.0;
+      if (W == 2 && eq + 1 < e_hi) {
+        const int u1 = (int)((bq >> 8) & 0x7Fu);
+        const long long r1 = rows[q] + (js[q] + 1 >= k ? 1 : 0);
+        stream_store(reinterpret_cast<double2*>(o_from + eq), make_double2(f0, u1 > 0 ? (double)(r1 + 1) : 0.0));
+        stream_store(reinterpret_cast<double2*>(o_to + eq), make_double2(t0v, u1 > 0 ? (double)(t[q][W - 1] + 1) : 0.0));
+        stream_store(reinterpret_cast<double2*>(o_w + eq), make_double2(lut[u0], lut[u1]));
+      } else {
+        stream_store(o_from + eq, f0);
+        stream_store(o_to + eq, t0v);
+        stream_store(o_w + eq, lut[u0]);
+      }
     }
   }
 }
