@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--config", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="BASELINE.json configs[i-1]; cfg4 (4M x 30) is the one the metric is quoted on")
     ap.add_argument("--host-share", type=float, default=-1.0, help="N>1: host rank's row share (default: calibrated)")
+    ap.add_argument("--direct-share", type=float, default=-1.0,
+                    help="N>1: share of a peer's rows whose finished doubles the peer stores itself into rank 0's "
+                         "output (default: GFICF_CUDA_PEER_DIRECT or the built-in choice)")
     ap.add_argument("--no-traffic-probe", action="store_true", help="do not re-run the kernel under ncu for roofline.traffic")
     ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-parity", action="store_true")
@@ -382,7 +385,10 @@ def run_ours(a):
             share = 0.0
         if a.gather == "peer" and k <= 127:
             try:
-                pg = sharding.PeerGather(n, k, host_share=share)
+                pg = sharding.PeerGather(n, k, host_share=share,
+                                         direct_share=a.direct_share if a.direct_share >= 0 else None)
+                if pg.out3 is not None:  # the peer-store split: the output lives in the buffer the gather exports
+                    out = pg.out3
             except RuntimeError as ex:  # raised on every rank together
                 sys.stderr.write("bench.py: %s; falling back to NCCL send/recv\n" % ex)
                 a.gather = "nccl"
@@ -400,8 +406,9 @@ def run_ours(a):
                 "%.3f ms per 1M rows); resident replicated int32 index; ONE persistent count launch per rank whose "
                 "epilogue stores the parity-tagged u8 counts into rank 0's HBM (CUDA IPC mapping over NVLink); rank 0: "
                 "fused kernel on its own rows, then ONE streaming expand launch that polls the count bytes (no flags, "
-                "no per-chunk launches)" % (world, 100.0 * host_share, t_fused * 1e6 / m, t_count * 1e6 / m,
-                                           t_expand * 1e6 / m))
+                "no per-chunk launches); peer-store share %.0f%% (finished doubles of a peer's last rows stored by the "
+                "peer itself into rank 0's output)" % (world, 100.0 * host_share, t_fused * 1e6 / m, t_count * 1e6 / m,
+                                                        t_expand * 1e6 / m, 100.0 * pg.direct_share))
         else:
             counts_all = torch.empty(E, dtype=torch.uint8 if k <= 255 else torch.int16, device=dev)
             pg = sharding.PipelinedGather(n, k, rho=t_expand / t_count, chunks=a.chunks)

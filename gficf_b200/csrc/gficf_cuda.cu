@@ -132,12 +132,16 @@ int wide_log_ts(int k) {
 
 size_t wide_smem_bytes(int log_ts) { return (size_t)wide_smem_words(log_ts) * 4 + 129 * sizeof(double); }
 
-// persistent grid: resident CTAs per SM x SM count, capped by the work
+// persistent grid: resident CTAs per SM x SM count, capped by the work.  tl_cta_cap (> 0) lowers the
+// CTAs per SM so that two persistent kernels on different streams can be resident side by side
+// (gficf_cuda_set_launch_ctas_per_sm).
+thread_local int tl_cta_cap = 0;
 template <typename K>
 int persistent_grid(K kernel, int block, size_t smem, long long work_ctas) {
   int per_sm = 0;
   CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
   if (per_sm < 1) per_sm = 1;
+  if (tl_cta_cap > 0 && per_sm > tl_cta_cap) per_sm = tl_cta_cap;
   long long g = (long long)per_sm * sm_count();
   if (g > work_ctas) g = work_ctas;
   if (g < 1) g = 1;
@@ -1205,6 +1209,12 @@ int gficf_cuda_expand_host(const void* idx_colmajor, int32_t elem_bytes, int64_t
       }
     });
   for (auto& t : pool) t.join();
+  return GFICF_OK;
+}
+
+int gficf_cuda_set_launch_ctas_per_sm(int32_t ctas_per_sm) {
+  if (ctas_per_sm < 0) return GFICF_E_ARG;
+  tl_cta_cap = ctas_per_sm;
   return GFICF_OK;
 }
 

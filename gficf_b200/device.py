@@ -206,3 +206,32 @@ def expand_stream(idx_i32: torch.Tensor, k: int, segments, counts_ptr: int, out3
         _lib.check(_lib.lib().gficf_cuda_expand_stream_dev(idx_i32.data_ptr(), k, lo, hi, len(segs), counts_ptr,
                                                            out3[0].data_ptr(), out3[1].data_ptr(), out3[2].data_ptr(),
                                                            tag, int(timeout_ms), flags.data_ptr(), _stream_ptr()))
+
+
+def jaccard_edges_to(idx_i32: torch.Tensor, n: int, k: int, row_lo: int, row_hi: int, from_ptr: int, to_ptr: int,
+                     w_ptr: int, flags: torch.Tensor) -> None:
+    """Fused kernel for rows [row_lo,row_hi) writing (from, to, w) at raw device addresses (the slab's
+    first element each; may be a peer GPU's memory: the host rank's mapped output)."""
+    _require_cuda(idx_i32, torch.int32)
+    with torch.cuda.device(idx_i32.device):
+        _lib.check(_lib.lib().gficf_cuda_jaccard_dev(idx_i32.data_ptr(), n, k, row_lo, row_hi, from_ptr, to_ptr, w_ptr,
+                                                     flags.data_ptr(), _stream_ptr()))
+
+
+def set_launch_cap(ctas_per_sm: int) -> None:
+    """Cap the resident CTAs per SM of the persistent kernels launched from this thread (0 = none)."""
+    _lib.check(_lib.lib().gficf_cuda_set_launch_ctas_per_sm(int(ctas_per_sm)))
+
+
+class _DeviceBuffer:
+    """A raw device allocation presented through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def tensor_from_ptr(ptr: int, shape, dtype=torch.float64) -> torch.Tensor:
+    """torch view of device memory the library allocated (e.g. gficf_cuda_ipc_alloc), current device."""
+    typestr = {torch.float64: "<f8", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_DeviceBuffer(ptr, shape, typestr), device=torch.device("cuda", torch.cuda.current_device()))

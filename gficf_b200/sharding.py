@@ -300,11 +300,18 @@ class PeerGather:
     The only other synchronisation is one ack flag per step: a peer may overwrite the buffer for
     step s+1 only after the host rank's expand of step s has finished.
 
-    torch.distributed only carries the 64-byte IPC handle at construction and the flag bits in
-    finish()."""
+    direct_share > 0 (the peer-store split): the host rank writes 24 B per edge of the WHOLE matrix,
+    which bounds this mode from ~6 ranks on.  A peer then counts only the first (1 - direct_share) of
+    its rows (3 CTAs per SM) while a second, 1-CTA-per-SM launch of the FUSED kernel on a side stream
+    stores the finished doubles of its last rows straight into the host rank's output over NVLink
+    (peer-mapped output, one completion flag per peer and step); the host rank expands less.  The
+    output then lives in a buffer this object allocates and exports (`out3`).
+
+    torch.distributed only carries the IPC handles at construction and the flag bits in finish()."""
 
     def __init__(self, n: int, k: int, group=None, host_share: float | None = None, host_rank: int = 0,
-                 timeout_ms: int = 0, rho: float | None = None, chunks: int | None = None):
+                 timeout_ms: int = 0, rho: float | None = None, chunks: int | None = None,
+                 direct_share: float | None = None):
         from . import device as D
 
         if k > 127:
@@ -318,6 +325,14 @@ class PeerGather:
                                              rho if rho is not None else 0.2)
         self.host_share = host_share
         self.bounds = share_bounds(n, self.world, host_share, host_rank, align=16)
+        if direct_share is None:
+            direct_share = float(os.environ.get("GFICF_CUDA_PEER_DIRECT", "0") or 0.0)
+        self.direct_share = min(0.9, max(0.0, direct_share)) if k <= 32 else 0.0  # the k <= 32 kernels only
+        # [lo, mid): counted, expanded by the host rank; [mid, hi): finished doubles stored by the peer itself
+        self.mids = []
+        for r, (lo, hi) in enumerate(self.bounds):
+            d = 0 if r == host_rank else int(round(self.direct_share * (hi - lo))) // 16 * 16
+            self.mids.append(hi - d)
         self.timeout_ms = timeout_ms
         self.epoch = 0
         self.launches = 0
@@ -333,12 +348,19 @@ class PeerGather:
         e = n * k
         self.flag_off = (e + 255) // 256 * 256          # the ack flag (+ one done flag per rank) lives behind the counts
         nbytes = self.flag_off + 256
+        self.out3 = None
+        self.out_base = 0
+        self.side = torch.cuda.Stream() if self.direct_share > 0 and self.rank != host_rank else None
         box = [None]
         ok, self.base = 1, 0
         if self.rank == host_rank:
             try:
                 self.base, handle = D.ipc_alloc(nbytes)   # zero-filled: parity 0, the first step uses 0x80
-                box = [handle]
+                h_out = None
+                if self.direct_share > 0:
+                    self.out_base, h_out = D.ipc_alloc(3 * e * 8)
+                    self.out3 = D.tensor_from_ptr(self.out_base, (3, e), torch.float64)
+                box = [(handle, h_out)]
             except Exception:
                 ok = 0
         dist.broadcast_object_list(box, src=host_rank, group=group)
@@ -346,18 +368,27 @@ class PeerGather:
             try:
                 if box[0] is None:
                     raise RuntimeError("no handle")
-                self.base = D.ipc_open(box[0])
+                self.base = D.ipc_open(box[0][0])
+                if self.direct_share > 0:
+                    self.out_base = D.ipc_open(box[0][1])
             except Exception:
                 ok = 0
         self.flags = D.new_flags(torch.device("cuda", torch.cuda.current_device()))
-        # every rank learns whether EVERY rank could map the buffer (no peer access between some
+        # every rank learns whether EVERY rank could map the buffers (no peer access between some
         # GPUs, IPC disabled in a container ...): all raise together, the caller falls back to NCCL
         agree = torch.tensor([ok], dtype=torch.int32, device=self.flags.device)
         dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=group)
         if int(agree[0]) == 0:
-            if self.base:
-                (D.ipc_free if self.rank == host_rank else D.ipc_close)(self.base)
+            self._release()
             raise RuntimeError("peer-memory gather unavailable: the count buffer could not be mapped on every rank")
+
+    def _release(self):
+        D = self.D
+        self.out3 = None
+        for ptr in (self.base, self.out_base):
+            if ptr:
+                (D.ipc_free if self.rank == self.host else D.ipc_close)(ptr)
+        self.base = self.out_base = 0
 
     def rows_of(self, rank: int) -> int:
         return self.bounds[rank][1] - self.bounds[rank][0]
@@ -365,28 +396,43 @@ class PeerGather:
     def close(self):
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
-        if self.rank == self.host:
-            self.D.ipc_free(self.base)
-        else:
-            self.D.ipc_close(self.base)
+        self._release()
 
-    def step(self, idx_full, out3):
-        """One pass: asynchronous on the current stream.  out3: float64 [3, n*k] on the host rank."""
+    def step(self, idx_full, out3=None):
+        """One pass: asynchronous on the current stream.  out3: float64 [3, n*k] on the host rank
+        (ignored with direct_share > 0: the output is self.out3)."""
         D, k, n = self.D, self.k, self.n
         self.epoch += 1
         tag = (self.epoch & 1) << 7
         ack = self.base + self.flag_off
         lo, hi = self.bounds[self.rank]
+        mid = self.mids[self.rank]
         if self.rank != self.host:
             # the host rank must have expanded the previous step's counts before they are overwritten
             D.wait_flag(ack, self.epoch - 1, self.flags)
-            if hi > lo:
-                D.jaccard_counts_tagged_to(idx_full, n, k, lo, hi, self.base + lo * k,
+            main = torch.cuda.current_stream()
+            if hi > mid:  # the peer-store share: fused kernel on a side stream, 1 CTA per SM, next to the count kernel
+                self.side.wait_stream(main)
+                D.set_launch_cap(3)
+            if mid > lo:
+                D.jaccard_counts_tagged_to(idx_full, n, k, lo, mid, self.base + lo * k,
                                            tag | (0x100 if self.row_stores else 0), self.flags)
                 self.launches += 1
-            if self.mode == "wait":
+            if hi > mid:
+                e = n * k
+                with torch.cuda.stream(self.side):
+                    D.set_launch_cap(1)
+                    D.jaccard_edges_to(idx_full, n, k, mid, hi, self.out_base + 8 * (mid * k),
+                                       self.out_base + 8 * (e + mid * k), self.out_base + 8 * (2 * e + mid * k), self.flags)
+                    D.signal(ack + 4 * (1 + self.rank), self.epoch)
+                D.set_launch_cap(0)
+                main.wait_stream(self.side)
+                self.launches += 1
+            elif self.mode == "wait":
                 D.signal(ack + 4 * (1 + self.rank), self.epoch)
             return
+        if self.direct_share > 0:
+            out3 = self.out3
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if self.trace is not None else None
         if ev:
             ev[0].record()
@@ -395,7 +441,7 @@ class PeerGather:
             self.launches += 1
         if ev:
             ev[1].record()
-        segs = [b for r, b in enumerate(self.bounds) if r != self.host and b[1] > b[0]]
+        segs = [(b[0], self.mids[r]) for r, b in enumerate(self.bounds) if r != self.host and self.mids[r] > b[0]]
         if self.mode == "wait":
             for r in range(self.world):
                 if r != self.host:
@@ -403,18 +449,24 @@ class PeerGather:
         if segs:
             D.expand_stream(idx_full, k, segs, self.base, out3, tag, self.flags, self.timeout_ms)
             self.launches += 1
+        if self.direct_share > 0 and self.mode != "wait":  # the peers' own stores must have landed
+            for r in range(self.world):
+                if r != self.host and self.bounds[r][1] > self.mids[r]:
+                    D.wait_flag(ack + 4 * (1 + r), self.epoch, self.flags)
         D.signal(ack, self.epoch)
         if ev:
             ev[2].record()
             self.trace.append(ev)
 
-    def finish(self, idx_full, out3) -> int:
+    def finish(self, idx_full, out3=None) -> int:
         """Collective, after the last step(): agrees on the flag bits of all ranks.  A peer timeout
         raises on every rank (the output is invalid); rows with repeated ids (DUP_ID / HASH_FAIL on
         any rank invalidate fast counts everywhere) are recomputed by the host rank with the exact
         multiset kernel + expand.  Returns the OR of the flags."""
         D = self.D
-        torch.cuda.current_stream().synchronize()
+        if self.direct_share > 0:
+            out3 = self.out3
+        torch.cuda.synchronize()
         bits = torch.stack([(self.flags[0] >> b) & 1 for b in range(4)])
         dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=self.group)
         allf = int(bits[0]) | (int(bits[1]) << 1) | (int(bits[2]) << 2) | (int(bits[3]) << 3)

@@ -324,6 +324,12 @@ int gficf_cuda_snn_lower(const void* idx_colmajor, int32_t elem_bytes, int64_t n
 int gficf_cuda_wmu_test(const double* mat_x, const double* mat_y, int64_t n_genes, int64_t n1, int64_t n2,
                         double* out, char* err, size_t errlen);
 
+/* Caps the resident CTAs per SM of the persistent Jaccard kernels launched from THIS thread (0 = what
+ * the occupancy allows: the default).  For callers that run two of them side by side on different
+ * streams: the peer gather's peers count most of their rows with 3 CTAs per SM while a 1-CTA-per-SM
+ * fused kernel stores finished doubles of the other rows straight into the host rank's output. */
+int gficf_cuda_set_launch_ctas_per_sm(int32_t ctas_per_sm);
+
 /* Launch geometry of the last fast-kernel launch on this thread (for the
  * bench record): grid, block, dynamic smem bytes, kernels launched. */
 int gficf_cuda_last_launch(int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* variant);

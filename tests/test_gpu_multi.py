@@ -102,6 +102,22 @@ for n, k, rho in ((300_000, 30, 0.19), (50_001, 15, 0.6), (20_000, 100, 0.0), (7
             ref1, _ = D.jaccard_edges(padded, n, k)
             assert torch.equal(o3, ref1), ("peer", n, k, share, host)
         peer.close()
+# the peer-store split: peers store finished doubles of their last rows straight into the host rank's output
+for n, k, ds, host in ((300_000, 30, 0.25, 0), (50_001, 15, 0.5, dist.get_world_size() - 1), (40_000, 7, 0.1, 0)):
+    idx0 = synth.knn_index(n, k, scramble=True, device="cuda")
+    padded, fl = D.pad_rows(idx0)
+    peer = sharding.PeerGather(n, k, host_share=0.1, host_rank=host, timeout_ms=5000, direct_share=ds)
+    assert (peer.out3 is not None) == (rank == host)
+    if rank == host:
+        peer.out3.fill_(-1.0)
+    torch.cuda.synchronize(); dist.barrier()
+    for it in range(3):
+        peer.step(padded)
+    assert peer.finish(padded) == 0
+    if rank == host:
+        ref1, _ = D.jaccard_edges(padded, n, k)
+        assert torch.equal(peer.out3, ref1), ("peer-store split", n, k, ds, host)
+    peer.close()
 # streaming peer gather: a repeated id anywhere -> finish() reruns the exact path on the host rank
 n, k = 40_000, 30
 idx0 = synth.knn_index(n, k, scramble=True, device="cuda")
