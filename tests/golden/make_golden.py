@@ -40,7 +40,36 @@ def cases():
     yield "dup_row_5_5", np.array([[2, 2], [2, 3], [1, 1]], dtype=np.float64)
 
 
+def wmu_cases():
+    """Mann-Whitney fixtures: (name, matX, matY)."""
+    rng = np.random.default_rng(180582)
+
+    def sc(genes, cells, density, integer=False):
+        m = rng.gamma(2.0, 50.0, size=(genes, cells)) * (rng.random((genes, cells)) < density)
+        return np.floor(m / 40.0) if integer else m
+
+    m = sc(24, 260, 0.2)
+    m[0, :] = 3.0          # one tie group -> p = 1
+    m[1, :] = 0.0
+    m[2, :60] = 0.0        # complete separation
+    m[2, 60:] = rng.random(200) + 1.0
+    m[3, ::2] = -0.0       # -0.0 ties with +0.0
+    yield "wmu_sparse_24x60_200", m[:, :60], m[:, 60:]
+    m = sc(16, 96, 0.6, integer=True)
+    yield "wmu_integer_ties_16x32_64", m[:, :32], m[:, 32:]
+    m = rng.normal(size=(10, 41))
+    yield "wmu_dense_negative_10x1_40", m[:, :1], m[:, 1:]
+
+
 def main():
+    from oracle.binding import WmuReference
+
+    wref = WmuReference()
+    for name, x, y in wmu_cases():
+        x, y = np.asfortranarray(x, dtype=np.float64), np.asfortranarray(y, dtype=np.float64)
+        out = wref.wmu(x, y, nthreads=1)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x, y=y, out=out)
+        print(name, x.shape, y.shape, "p in [%.3g, %.3g]" % (np.nanmin(out[:, 0]), np.nanmax(out[:, 0])))
     ref = Reference()
     for name, idx in cases():
         idx = np.asfortranarray(idx, dtype=np.float64)

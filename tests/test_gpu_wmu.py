@@ -8,9 +8,16 @@ import numpy as np
 import pytest
 
 from oracle.binding import WmuOracle
-from tests.test_wmu_oracle import sc_matrix
+from tests.test_wmu_oracle import WMU_GOLDEN, sc_matrix
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("path", WMU_GOLDEN, ids=[__import__("os").path.basename(p)[:-4] for p in WMU_GOLDEN])
+def test_wmu_golden_vectors(cuda, path):
+    """Outputs of the reference itself (tests/golden/make_golden.py)."""
+    g = np.load(path)
+    assert np.array_equal(cuda.rcpp_parallel_WMU_test(g["x"], g["y"]), g["out"], equal_nan=True)
 
 
 def _check(cuda, x, y):

@@ -10,7 +10,12 @@ import pytest
 from scipy import stats
 from scipy.special import ndtr
 
+import glob
+import os
+
 from oracle.binding import WmuOracle, WmuReference
+
+WMU_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "wmu_*.npz")))
 
 
 def sc_matrix(rng, genes, cells, density=0.15, integer=False):
@@ -64,3 +69,11 @@ def test_oracle_against_scipy_mannwhitneyu():
         ref = stats.mannwhitneyu(x[g], y[g], alternative="two-sided", method="asymptotic", use_continuity=True)
         assert abs(got[g, 0] - ref.pvalue) <= 1e-9 * max(ref.pvalue, 1e-300) + 1e-15
         assert abs(got[g, 1] - np.log2((x[g] + 1).mean() / (y[g] + 1).mean())) < 1e-12
+
+
+@pytest.mark.parametrize("path", WMU_GOLDEN, ids=[os.path.basename(p)[:-4] for p in WMU_GOLDEN])
+def test_oracle_equals_golden_vectors(path):
+    """Outputs of the reference's own sources (tests/golden/make_golden.py), committed so that the pin
+    also holds where /root/reference does not exist."""
+    g = np.load(path)
+    assert np.array_equal(WmuOracle().wmu(g["x"], g["y"]), g["out"], equal_nan=True)
