@@ -1632,6 +1632,7 @@ int gficf_cuda_expand_stream_dev(const int32_t* d_idx_i32, int32_t k, const int6
   int per_sm = 0;
   if (pair) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_stream_kernel<2>, kExpandThreads, 0));
   else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_stream_kernel<1>, kExpandThreads, 0));
+  if (tl_cta_cap > 0 && per_sm > tl_cta_cap) per_sm = tl_cta_cap;  // leave room for a kernel on another stream
   long long gx = std::max<long long>(1, (long long)sm_count() * std::max(1, per_sm) / ns);
   gx = std::min<long long>(gx, (longest / w + kExpandThreads - 1) / kExpandThreads);
   gx = std::max<long long>(gx, 1);

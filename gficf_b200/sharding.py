@@ -345,6 +345,13 @@ class PeerGather:
         st = os.environ.get("GFICF_CUDA_PEER_STORE", "auto")
         self.row_stores = st == "bytes" or (st == "auto" and self.world < 6)
         self.trace = None  # set to [] to collect (start, mid, end) CUDA events of every host-rank step
+        # host rank, "side": its own rows are computed by a capped fused launch on a side stream NEXT TO the
+        # streaming expand (which mostly waits for the peers at 3-5 ranks) instead of before it.
+        # GFICF_CUDA_HOST_OWN = "first" (default) | "side:<fused CTAs per SM>:<expand CTAs per SM>"
+        own = os.environ.get("GFICF_CUDA_HOST_OWN", "first").split(":")
+        self.host_side = own[0] == "side"
+        self.host_side_caps = (int(own[1]) if len(own) > 1 else 1, int(own[2]) if len(own) > 2 else 4)
+        self.side_host = torch.cuda.Stream() if self.host_side and self.rank == host_rank else None
         e = n * k
         self.flag_off = (e + 255) // 256 * 256          # the ack flag (+ one done flag per rank) lives behind the counts
         nbytes = self.flag_off + 256
@@ -436,7 +443,16 @@ class PeerGather:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if self.trace is not None else None
         if ev:
             ev[0].record()
-        if hi > lo:  # own rows: fused kernel straight into the output, while the peers count
+        side = self.side_host if (self.host_side and hi > lo) else None
+        if side is not None:  # own rows on a side stream, capped, next to the expand
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                D.set_launch_cap(self.host_side_caps[0])
+                D.jaccard_edges(idx_full, n, k, lo, hi, out=out3[:, lo * k:hi * k], flags=self.flags)
+            D.set_launch_cap(self.host_side_caps[1])
+            self.launches += 1
+        elif hi > lo:  # own rows: fused kernel straight into the output, while the peers count
             D.jaccard_edges(idx_full, n, k, lo, hi, out=out3[:, lo * k:hi * k], flags=self.flags)
             self.launches += 1
         if ev:
@@ -449,6 +465,9 @@ class PeerGather:
         if segs:
             D.expand_stream(idx_full, k, segs, self.base, out3, tag, self.flags, self.timeout_ms)
             self.launches += 1
+        if side is not None:
+            D.set_launch_cap(0)
+            torch.cuda.current_stream().wait_stream(side)
         if self.direct_share > 0 and self.mode != "wait":  # the peers' own stores must have landed
             for r in range(self.world):
                 if r != self.host and self.bounds[r][1] > self.mids[r]:
