@@ -27,7 +27,7 @@
 //     from/to/w with coalesced streaming stores (st.global.cs) so that the
 //     output does not evict the index matrix from L2.
 #pragma once
-#include <cuda_runtime.h>
+#include "scan_kernels.cuh"
 
 // tuning knobs (overridable with -D for A/B runs; defaults are the measured best)
 #ifndef GFICF_SMALL_LOG_TS32
@@ -51,7 +51,6 @@ namespace gficf {
 
 constexpr int kPadId = -2;              // pad entries of an index row (never equals an id or kEmpty)
 constexpr unsigned kEmpty = 0xFFFFFFFFu;  // empty hash slot
-constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr unsigned kFlagBadId = 1u, kFlagDupId = 2u, kFlagHashFail = 4u;
 constexpr int kMaxTries = 256;
 constexpr unsigned kMult0 = 0x9E3779B1u;  // odd; successive multipliers come from an LCG
@@ -1008,44 +1007,6 @@ compact_count_kernel(const CT* __restrict__ d_u, long long total, long long* __r
     for (int w = 0; w < kCompactThreads / 32; ++w) s += wsum[w];
     chunk_cnt[blockIdx.x] = s;
   }
-}
-
-// exclusive scan of chunk counts in place, single CTA; total -> *n_written
-__global__ void __launch_bounds__(1024)
-compact_scan_kernel(long long* __restrict__ chunk_cnt, long long nchunks,
-                    long long* __restrict__ n_written) {
-  __shared__ long long wtot[32];
-  __shared__ long long carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long b = 0; b < nchunks; b += 1024) {
-    const long long x = b + threadIdx.x;
-    const long long v = x < nchunks ? chunk_cnt[x] : 0;
-    long long inc = v;
-    for (int m = 1; m < 32; m <<= 1) {
-      const long long o = __shfl_up_sync(kFull, inc, m);
-      if (lane >= m) inc += o;
-    }
-    if (lane == 31) wtot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      long long w = wtot[lane];
-      for (int m = 1; m < 32; m <<= 1) {
-        const long long o = __shfl_up_sync(kFull, w, m);
-        if (lane >= m) w += o;
-      }
-      wtot[lane] = w;  // inclusive over warps
-    }
-    __syncthreads();
-    const long long carry = carry_s;
-    const long long before = carry + (warp ? wtot[warp - 1] : 0) + inc - v;
-    if (x < nchunks) chunk_cnt[x] = before;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + wtot[31];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *n_written = carry_s;
 }
 
 template <typename CT>

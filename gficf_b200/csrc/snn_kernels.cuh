@@ -166,52 +166,6 @@ snn_edges_kernel(const int* __restrict__ idx, const uint8_t* __restrict__ um, lo
   }
 }
 
-// exclusive scan of int32 counts into int64 offsets: per-block sums, scan of the sums
-// (compact_scan_kernel), block-local scan + offset
-constexpr int kScanBlock = 1024;
-
-__global__ void __launch_bounds__(kScanBlock)
-scan_block_sums_kernel(const int* __restrict__ cnt, long long n, long long* __restrict__ block_sums) {
-  __shared__ long long ws[32];
-  const long long x = (long long)blockIdx.x * kScanBlock + threadIdx.x;
-  long long v = x < n ? cnt[x] : 0;
-  for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    long long s = ws[threadIdx.x];
-    for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(kFull, s, m);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
-  }
-}
-
-__global__ void __launch_bounds__(kScanBlock)
-scan_finish_kernel(const int* __restrict__ cnt, long long n, const long long* __restrict__ block_off,
-                   const long long* __restrict__ total, long long* __restrict__ colptr) {
-  __shared__ long long ws[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long x = (long long)blockIdx.x * kScanBlock + threadIdx.x;
-  const long long v = x < n ? cnt[x] : 0;
-  long long inc = v;
-  for (int m = 1; m < 32; m <<= 1) {
-    const long long o = __shfl_up_sync(kFull, inc, m);
-    if (lane >= m) inc += o;
-  }
-  if (lane == 31) ws[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    long long s = ws[lane];
-    for (int m = 1; m < 32; m <<= 1) {
-      const long long o = __shfl_up_sync(kFull, s, m);
-      if (lane >= m) s += o;
-    }
-    ws[lane] = s;
-  }
-  __syncthreads();
-  if (x < n) colptr[x] = block_off[blockIdx.x] + (warp ? ws[warp - 1] : 0) + inc - v;
-  if (x == 0) colptr[n] = *total;
-}
-
 // ---------------------------------------------------------------------------
 // Rows ascending inside every column (the staged entries of a column are in atomic arrival order).
 //   deg <= 32    one warp, bitonic network over the lanes (shuffles)

@@ -22,6 +22,7 @@ ORACLE_SO = os.path.join(_HERE, "libgficf_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libgficf_ref.so")
 REF_WMU_SO = os.path.join(_HERE, "_ref", "libgficf_ref_wmu.so")
 MODOPT_BIN = os.path.join(_HERE, "_ref", "modopt")
+REF_MODOPT_SO = os.path.join(_HERE, "_ref", "libgficf_ref_modopt.so")
 
 _dp = C.POINTER(C.c_double)
 
@@ -206,3 +207,142 @@ class WmuReference:
         out = np.empty((g, 2), dtype=np.float64, order="F")
         self.last_seconds = self.lib.gficf_ref_wmu(_ptr(x), _ptr(y), g, x.shape[1], y.shape[1], _ptr(out), 0, nthreads)
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# The data-parallel pieces of the community detection: network from the
+# lower-triangle edge list, quality function, reduced network.  A network is the dict
+#   n_nodes, first (int32[n_nodes+1]), neighbor (int32[E]), edge_w (f64[E]), node_w (f64[n_nodes]),
+#   total_w (getTotalEdgeWeight), self_links (totalEdgeWeightSelfLinks)
+# ---------------------------------------------------------------------------------------------
+_ip = C.POINTER(C.c_int32)
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _pi(a: np.ndarray):
+    return a.ctypes.data_as(_ip)
+
+
+class NetworkOracle:
+    """oracle/modopt_oracle.c: our plain-C restatement of ModularityOptimizer.cpp:761-806, :462-482, :322-373."""
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build()
+        self.lib = C.CDLL(ORACLE_SO)
+        L = self.lib
+        L.modopt_network.argtypes = [_ip, _ip, _dp, C.c_longlong, C.c_int, _ip, _ip, _dp, _dp, _dp]
+        L.modopt_network.restype = C.c_longlong
+        L.modopt_quality.argtypes = [C.c_int, _ip, _ip, _dp, _dp, C.c_double, C.c_double, _ip, C.c_int,
+                                     C.c_double, _dp]
+        L.modopt_quality.restype = C.c_double
+        L.modopt_reduce.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _ip, C.c_int, _ip, _ip, _dp, _dp, _dp]
+        L.modopt_reduce.restype = C.c_longlong
+
+    def network(self, node1, node2, w) -> dict:
+        a, b, ww = _i32(node1), _i32(node2), _f64(w)
+        m = a.size
+        n_nodes = int(max(a.max(), b.max())) + 1
+        first = np.zeros(n_nodes + 1, np.int32)
+        neighbor = np.zeros(2 * m, np.int32)
+        edge_w = np.zeros(2 * m, np.float64)
+        node_w = np.zeros(n_nodes, np.float64)
+        total = C.c_double(0.0)
+        e = self.lib.modopt_network(_pi(a), _pi(b), _ptr(ww), m, n_nodes, _pi(first), _pi(neighbor),
+                                    _ptr(edge_w), _ptr(node_w), C.byref(total))
+        return dict(n_nodes=n_nodes, first=first, neighbor=neighbor[:e].copy(), edge_w=edge_w[:e].copy(),
+                    node_w=node_w, total_w=total.value, self_links=0.0)
+
+    def quality(self, net: dict, cluster, resolution: float):
+        cl = _i32(cluster)
+        nc = int(cl.max()) + 1
+        cw = np.zeros(nc, np.float64)
+        q = self.lib.modopt_quality(net["n_nodes"], _pi(net["first"]), _pi(net["neighbor"]), _ptr(net["edge_w"]),
+                                    _ptr(net["node_w"]), net["self_links"], net["total_w"], _pi(cl), nc,
+                                    float(resolution), _ptr(cw))
+        return q, cw
+
+    def reduce(self, net: dict, cluster) -> dict:
+        cl = _i32(cluster)
+        nc = int(cl.max()) + 1
+        e = max(1, net["neighbor"].size)
+        first = np.zeros(nc + 1, np.int32)
+        neighbor = np.zeros(e, np.int32)
+        edge_w = np.zeros(e, np.float64)
+        node_w = np.zeros(nc, np.float64)
+        self_links = C.c_double(net["self_links"])
+        n_red = self.lib.modopt_reduce(net["n_nodes"], _pi(net["first"]), _pi(net["neighbor"]), _ptr(net["edge_w"]),
+                                       _ptr(net["node_w"]), _pi(cl), nc, _pi(first), _pi(neighbor), _ptr(edge_w),
+                                       _ptr(node_w), C.byref(self_links))
+        ew = edge_w[:n_red].copy()
+        return dict(n_nodes=nc, first=first, neighbor=neighbor[:n_red].copy(), edge_w=ew, node_w=node_w,
+                    total_w=_seq_sum(ew) / 2.0,
+                    self_links=self_links.value)
+
+
+def _seq_sum(x: np.ndarray) -> float:
+    """std::accumulate(first, last, 0.0): strictly left to right (numpy's sum is pairwise)."""
+    s = 0.0
+    for v in x.tolist():
+        s += v
+    return s
+
+
+class NetworkReference:
+    """The reference's own Network / Clustering / VOSClusteringTechnique classes (oracle/_ref)."""
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_MODOPT_SO)
+
+    def __init__(self):
+        if not os.path.exists(REF_MODOPT_SO):
+            raise FileNotFoundError(REF_MODOPT_SO + " (build it in the container: make -C oracle ref)")
+        self.lib = C.CDLL(REF_MODOPT_SO)
+        L = self.lib
+        L.ref_net_build.argtypes = [_ip, _ip, _dp, C.c_longlong, C.c_int]
+        L.ref_net_build.restype = C.c_void_p
+        L.ref_net_dims.argtypes = [C.c_void_p, _ip, _ip]
+        L.ref_net_dims.restype = None
+        L.ref_net_get.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp, _dp]
+        L.ref_net_get.restype = None
+        L.ref_net_quality.argtypes = [C.c_void_p, _ip, C.c_double]
+        L.ref_net_quality.restype = C.c_double
+        L.ref_net_reduce.argtypes = [C.c_void_p, _ip]
+        L.ref_net_reduce.restype = C.c_void_p
+        L.ref_net_free.argtypes = [C.c_void_p]
+        L.ref_net_free.restype = None
+
+    def _export(self, h) -> dict:
+        nn, ne = C.c_int32(0), C.c_int32(0)
+        self.lib.ref_net_dims(h, C.byref(nn), C.byref(ne))
+        first = np.zeros(nn.value + 1, np.int32)
+        neighbor = np.zeros(max(1, ne.value), np.int32)
+        edge_w = np.zeros(max(1, ne.value), np.float64)
+        node_w = np.zeros(nn.value, np.float64)
+        total, self_links = C.c_double(0.0), C.c_double(0.0)
+        self.lib.ref_net_get(h, _pi(first), _pi(neighbor), _ptr(edge_w), _ptr(node_w), C.byref(total),
+                             C.byref(self_links))
+        return dict(n_nodes=nn.value, first=first, neighbor=neighbor[:ne.value].copy(),
+                    edge_w=edge_w[:ne.value].copy(), node_w=node_w, total_w=total.value,
+                    self_links=self_links.value, handle=h)
+
+    def network(self, node1, node2, w) -> dict:
+        a, b, ww = _i32(node1), _i32(node2), _f64(w)
+        return self._export(self.lib.ref_net_build(_pi(a), _pi(b), _ptr(ww), a.size, 1))
+
+    def quality(self, net: dict, cluster, resolution: float) -> float:
+        return self.lib.ref_net_quality(net["handle"], _pi(_i32(cluster)), float(resolution))
+
+    def reduce(self, net: dict, cluster) -> dict:
+        return self._export(self.lib.ref_net_reduce(net["handle"], _pi(_i32(cluster))))
+
+    def free(self, net: dict) -> None:
+        self.lib.ref_net_free(net.pop("handle"))

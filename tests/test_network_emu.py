@@ -1,0 +1,302 @@
+"""The network kernels (gficf_b200/csrc/network_kernels.cuh) and their launch sequences
+(network_plan.h) run on the CPU through tests/cuda_emu -- a fibre-per-thread emulation of CTAs,
+barriers and warp collectives -- against the oracle and the reference's own classes.  This is the
+no-GPU check of the code that tests/test_gpu_network.py runs on the B200."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.network_cases import REL, assert_same_network, random_lower, to_csc
+from oracle.binding import NetworkOracle, NetworkReference
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ll, _ip, _dp, _up, _ullp = (C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                             C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong))
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libnetwork_emu.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-DGFICF_CUDA_EMU", "-I" + os.path.join(ROOT, "tests", "cuda_emu"),
+           "-I" + os.path.join(ROOT, "gficf_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-Wall", "-Werror",
+           os.path.join(ROOT, "tests", "cuda_emu", "network_emu.cpp"), "-o", so]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    L = C.CDLL(so)
+    L.emu_scan.argtypes = [_ip, C.c_longlong, _ll]
+    L.emu_radix_sort.argtypes = [_ullp, _up, C.c_longlong, C.c_int, C.c_int]
+    L.emu_sum.argtypes = [_dp, C.c_longlong, C.c_double]
+    L.emu_sum.restype = C.c_double
+    L.emu_net_build.argtypes = [_ll, _ip, _dp, C.c_longlong, C.c_longlong, _ll, _ip, _dp, _dp, _dp, C.c_int]
+    L.emu_net_build.restype = C.c_uint
+    L.emu_net_quality.argtypes = [_ll, _ip, _dp, _dp, C.c_longlong, _ip, C.c_int, C.c_double, C.c_double,
+                                  C.c_double, _dp, _dp, C.c_int]
+    L.emu_net_quality.restype = C.c_uint
+    L.emu_net_reduce.argtypes = [_ll, _ip, _dp, _dp, C.c_longlong, _ip, C.c_int, _ll, _ip, _dp, C.c_longlong,
+                                 _dp, _dp, _dp, _ll, _up, C.c_int]
+    L.emu_net_reduce.restype = C.c_longlong
+    return L
+
+
+def emu_build(L, node1, node2, w, nv, ctas=3):
+    colptr, row = to_csc(node1, node2, nv)
+    nnz = row.size
+    first = np.zeros(nv + 1, np.int64)
+    neighbor = np.zeros(2 * nnz, np.int32)
+    edge_w = np.zeros(2 * nnz, np.float64)
+    node_w = np.zeros(nv, np.float64)
+    total = np.zeros(1, np.float64)
+    flags = L.emu_net_build(_p(colptr, _ll), _p(row, _ip), _p(w, _dp), nv, nnz, _p(first, _ll), _p(neighbor, _ip),
+                            _p(edge_w, _dp), _p(node_w, _dp), _p(total, _dp), ctas)
+    return dict(n_nodes=nv, first=first, neighbor=neighbor, edge_w=edge_w, node_w=node_w, total_w=float(total[0]),
+                self_links=0.0), flags
+
+
+def emu_quality(L, net, cluster, nc, resolution, ctas=3):
+    cw = np.zeros(nc, np.float64)
+    q = np.zeros(1, np.float64)
+    cl = np.ascontiguousarray(cluster, np.int32)
+    flags = L.emu_net_quality(_p(net["first"], _ll), _p(net["neighbor"], _ip), _p(net["edge_w"], _dp),
+                              _p(net["node_w"], _dp), net["n_nodes"], _p(cl, _ip), nc, resolution,
+                              net["self_links"], net["total_w"], _p(cw, _dp), _p(q, _dp), ctas)
+    return float(q[0]), cw, flags
+
+
+def emu_reduce(L, net, cluster, nc, ctas=3, r_cap=None):
+    cl = np.ascontiguousarray(cluster, np.int32)
+    cap = max(1, net["neighbor"].size) if r_cap is None else r_cap
+    r_first = np.zeros(nc + 1, np.int64)
+    r_neighbor = np.zeros(max(cap, 1), np.int32)
+    r_edge_w = np.zeros(max(cap, 1), np.float64)
+    r_node_w = np.zeros(nc, np.float64)
+    self_add = np.zeros(1, np.float64)
+    total = np.full(1, -1.0, np.float64)
+    needed = np.zeros(1, np.int64)
+    flags = np.zeros(1, np.uint32)
+    n = L.emu_net_reduce(_p(net["first"], _ll), _p(net["neighbor"], _ip), _p(net["edge_w"], _dp),
+                         _p(net["node_w"], _dp), net["n_nodes"], _p(cl, _ip), nc, _p(r_first, _ll),
+                         _p(r_neighbor, _ip), _p(r_edge_w, _dp), cap, _p(r_node_w, _dp), _p(self_add, _dp),
+                         _p(total, _dp), _p(needed, _ll), _p(flags, _up), ctas)
+    if n < 0:
+        return None, int(needed[0])
+    ew = r_edge_w[:n].copy()
+    return dict(n_nodes=nc, first=r_first, neighbor=r_neighbor[:n].copy(), edge_w=ew, node_w=r_node_w,
+                total_w=float(total[0]), self_links=net["self_links"] + float(self_add[0])), int(flags[0])
+
+
+def test_emulated_scan_sort_and_sum(emu):
+    rng = np.random.default_rng(0)
+    for m in [1, 31, 1024, 1025, 5000]:
+        cnt = rng.integers(0, 9, m).astype(np.int32)
+        out = np.zeros(m + 1, np.int64)
+        emu.emu_scan(_p(cnt, _ip), m, _p(out, _ll))
+        assert np.array_equal(out, np.concatenate([[0], np.cumsum(cnt)]))
+    for n, nbits, ctas in [(2, 3, 1), (100, 5, 3), (2048, 9, 3), (2049, 17, 1), (7000, 20, 2), (5000, 40, 3)]:
+        keys = rng.integers(0, 1 << nbits, n).astype(np.uint64)
+        vals = np.arange(n, dtype=np.uint32)
+        k2, v2 = keys.copy(), vals.copy()
+        emu.emu_radix_sort(_p(k2, _ullp), _p(v2, _up), n, nbits, ctas)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order]), (n, nbits)
+    for n in [0, 1, 255, 4097, 20000]:
+        x = rng.random(n)
+        assert abs(emu.emu_sum(_p(x, _dp), n, 0.5) - 0.5 * x.sum()) <= 1e-12 * max(1.0, x.sum())
+
+
+@pytest.mark.parametrize("nv,m,nc,seed", [(5, 6, 2, 1), (60, 300, 7, 2), (700, 6000, 40, 3), (1500, 9000, 300, 4),
+                                           (300, 9000, 3, 5)])
+def test_emulated_network_pipeline_matches_oracle(emu, nv, m, nc, seed):
+    rng = np.random.default_rng(seed)
+    n1, n2, w = random_lower(rng, nv, m)
+    nv = int(max(n1.max(), n2.max())) + 1
+    O = NetworkOracle()
+    want = O.network(n1, n2, w)
+    got, flags = emu_build(emu, n1, n2, w, nv)
+    assert flags == 0
+    assert_same_network(got, want)
+    assert abs(got["total_w"] - want["total_w"]) <= REL * want["total_w"]
+    # level 0: quality and reduced network for a random clustering that uses every cluster id
+    nc = min(nc, nv)
+    cl = rng.integers(0, nc, nv).astype(np.int32)
+    cl[rng.permutation(nv)[:nc]] = np.arange(nc)
+    res = 0.8 / (2 * want["total_w"])
+    q_want, cw_want = O.quality(want, cl, res)
+    q, cw, flags = emu_quality(emu, got, cl, nc, res)
+    assert flags == 0
+    assert np.array_equal(cw, cw_want)
+    assert abs(q - q_want) <= REL * max(1.0, abs(q_want))
+    red_want = O.reduce(want, cl)
+    red, flags = emu_reduce(emu, got, cl, nc)
+    assert flags == 0
+    assert_same_network(red, red_want)
+    # level 1 on the reduced network (self links now non-zero, weights are sums)
+    if nc >= 4:
+        nc2 = max(2, nc // 5)
+        cl2 = rng.integers(0, nc2, nc).astype(np.int32)
+        cl2[rng.permutation(nc)[:nc2]] = np.arange(nc2)
+        q2_want, cw2_want = O.quality(red_want, cl2, res)
+        q2, cw2, _ = emu_quality(emu, red, cl2, nc2, res)
+        assert np.array_equal(cw2, cw2_want)
+        assert abs(q2 - q2_want) <= REL * max(1.0, abs(q2_want))
+        red2_want = O.reduce(red_want, cl2)
+        red2, _ = emu_reduce(emu, red, cl2, nc2)
+        assert_same_network(red2, red2_want)
+
+
+def test_emulated_edge_cases(emu):
+    rng = np.random.default_rng(9)
+    n1, n2, w = random_lower(rng, 200, 1500)
+    nv = int(max(n1.max(), n2.max())) + 1
+    O = NetworkOracle()
+    want = O.network(n1, n2, w)
+    got, _ = emu_build(emu, n1, n2, w, nv, ctas=1)
+    # one cluster: no cross edge at all, everything becomes self links
+    one = np.zeros(nv, np.int32)
+    red, flags = emu_reduce(emu, got, one, 1)
+    red_want = O.reduce(want, one)
+    assert flags == 0 and red["neighbor"].size == 0
+    assert_same_network(red, red_want)
+    q, cw, _ = emu_quality(emu, got, one, 1, 0.01)
+    q_want, cw_want = O.quality(want, one, 0.01)
+    assert np.array_equal(cw, cw_want) and abs(q - q_want) <= REL
+    # singletons: the reduced network is the network itself
+    single = np.arange(nv, dtype=np.int32)
+    red, _ = emu_reduce(emu, got, single, nv)
+    assert_same_network(red, O.reduce(want, single))
+    assert np.array_equal(red["neighbor"], want["neighbor"])
+    # output capacity too small: the needed number of entries is reported, nothing is written past it
+    cl = rng.integers(0, 9, nv).astype(np.int32)
+    cl[:9] = np.arange(9)
+    none, needed = emu_reduce(emu, got, cl, 9, r_cap=3)
+    assert none is None and needed == O.reduce(want, cl)["neighbor"].size
+    # an entry that is not strictly lower, a row out of range, a non-positive weight: flagged
+    bad_row = n2.copy()
+    bad_row[5] = n1[5]
+    _, flags = emu_build(emu, n1, bad_row, w, nv)
+    assert flags & 64
+    wz = w.copy()
+    wz[7] = 0.0
+    _, flags = emu_build(emu, n1, n2, wz, nv)
+    assert flags & 32
+    bad_cl = cl.copy()
+    bad_cl[3] = 9
+    _, _, flags = emu_quality(emu, got, bad_cl, 9, 0.01)
+    assert flags & 64
+
+
+@pytest.mark.skipif(not NetworkReference.available(), reason="oracle/_ref not built")
+def test_emulated_pipeline_matches_reference_classes(emu):
+    """Same check against the reference's own Network / createReducedNetwork / calcQualityFunction."""
+    rng = np.random.default_rng(5)
+    n1, n2, w = random_lower(rng, 400, 3000)
+    nv = int(max(n1.max(), n2.max())) + 1
+    R = NetworkReference()
+    want = R.network(n1, n2, w)
+    got, _ = emu_build(emu, n1, n2, w, nv)
+    assert_same_network(got, want)
+    cl = rng.integers(0, 25, nv).astype(np.int32)
+    cl[:25] = np.arange(25)
+    res = 0.8 / (2 * want["total_w"])
+    q, _, _ = emu_quality(emu, got, cl, 25, res)
+    assert abs(q - R.quality(want, cl, res)) <= REL
+    red_want = R.reduce(want, cl)
+    red, _ = emu_reduce(emu, got, cl, 25)
+    assert_same_network(red, red_want)
+    R.free(red_want)
+    R.free(want)
+
+
+def test_python_mirror_over_the_emulated_abi(emu, monkeypatch):
+    """gficf_b200.modularity (the Python mirror of the reference's Network interface) driven end to
+    end on CPU tensors: the emulated library exports the same gficf_cuda_network_* entry points, so
+    every argument the mirror passes -- order, width, buffer sizes -- is checked without a GPU."""
+    import contextlib
+
+    import torch
+
+    from gficf_b200 import _lib, device as D, modularity
+
+    for name in ("gficf_cuda_network_scratch_bytes", "gficf_cuda_network_dev", "gficf_cuda_network_quality_dev",
+                 "gficf_cuda_network_reduce_dev"):
+        res, args = _lib.PROTOTYPES[name]
+        getattr(emu, name).restype = res
+        getattr(emu, name).argtypes = args
+    monkeypatch.setattr(_lib, "lib", lambda: emu)
+    monkeypatch.setattr(D, "_require_cuda", lambda t, dtype: None)
+    monkeypatch.setattr(D, "_stream_ptr", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+
+    rng = np.random.default_rng(11)
+    n1, n2, w = random_lower(rng, 500, 4000)
+    nv = int(max(n1.max(), n2.max())) + 1
+    colptr, row = to_csc(n1, n2, nv)
+    O = NetworkOracle()
+    want = O.network(n1, n2, w)
+    net = modularity.matrix_to_network(torch.from_numpy(colptr), torch.from_numpy(row), torch.from_numpy(w))
+
+    def as_dict(x):
+        return dict(n_nodes=x.n_nodes, first=x.first_neighbor_index.numpy(), neighbor=x.neighbor.numpy(),
+                    edge_w=x.edge_weight.numpy(), node_w=x.node_weight.numpy(), total_w=x.get_total_edge_weight(),
+                    self_links=x.total_edge_weight_self_links)
+
+    assert_same_network(as_dict(net), want)
+    cl = rng.integers(0, 12, nv).astype(np.int32)
+    cl[:12] = np.arange(12)
+    res = 0.8 / (2 * want["total_w"])
+    q_want, cw_want = O.quality(want, cl, res)
+    assert abs(net.calc_quality_function(cl, res) - q_want) <= REL
+    assert np.array_equal(net.cluster_weights(cl).numpy(), cw_want)
+    red_want = O.reduce(want, cl)
+    red = net.create_reduced_network(cl)
+    assert_same_network(as_dict(red), red_want)
+    cl2 = np.array([0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2], np.int32)
+    q2_want, _ = O.quality(red_want, cl2, res)
+    assert abs(red.calc_quality_function(cl2, res) - q2_want) <= REL
+    assert_same_network(as_dict(red.create_reduced_network(cl2)), O.reduce(red_want, cl2))
+    # flags surface as errors
+    bad = cl.copy()
+    bad[0] = 12
+    with pytest.raises(ValueError, match="cluster id"):
+        net.calc_quality_function(bad, res, n_clusters=12)
+    wz = w.copy()
+    wz[3] = -1.0
+    with pytest.raises(ValueError, match="> 0"):
+        modularity.matrix_to_network(torch.from_numpy(colptr), torch.from_numpy(row), torch.from_numpy(wz))
+    with pytest.raises(ValueError, match="no network data"):
+        modularity.matrix_to_network(torch.zeros(3, dtype=torch.int64), torch.zeros(0, dtype=torch.int32),
+                                     torch.zeros(0, dtype=torch.float64))
+
+
+def test_emulated_on_a_jaccard_graph_with_the_reference_louvain_labels(emu, oracle):
+    """The real input: the SNN graph of a planted kNN matrix (weights u/(2k-u), mutual pairs doubled)
+    and the clustering the reference's own Louvain run returns for it."""
+    from gficf_b200 import synth
+    from oracle import louvain
+    from oracle.binding import MODOPT_BIN
+
+    if not os.path.exists(MODOPT_BIN):
+        pytest.skip("oracle/_ref/modopt not built")
+    n, k = 1500, 10
+    rel = oracle.parallel(synth.to_r_matrix(synth.knn_index(n, k, family="planted", scramble=True)))
+    names, cols, rows, data = louvain.lower_triangle_edges(rel)
+    _, labels = louvain.louvain_labels(rel, n_start=2, n_iter=3)
+    O = NetworkOracle()
+    want = O.network(cols, rows, data)
+    got, flags = emu_build(emu, cols.astype(np.int32), rows.astype(np.int32), data, names.size)
+    assert flags == 0
+    assert_same_network(got, want)
+    cl = labels.astype(np.int32)
+    nc = int(cl.max()) + 1
+    res = 0.8 / (2 * want["total_w"])
+    q_want, cw_want = O.quality(want, cl, res)
+    q, cw, _ = emu_quality(emu, got, cl, nc, res)
+    assert np.array_equal(cw, cw_want) and abs(q - q_want) <= REL
+    red, _ = emu_reduce(emu, got, cl, nc)
+    assert_same_network(red, O.reduce(want, cl))
