@@ -70,11 +70,11 @@ PROTOTYPES = {
     "gficf_cuda_network_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "gficf_cuda_network_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
                                          C.c_size_t, _vp, _vp]),
-    "gficf_cuda_network_quality_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int32, C.c_double,
-                                                 C.c_double, _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
-    "gficf_cuda_network_reduce_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int32, _vp,
-                                                _vp, _vp, C.c_int64, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp,
-                                                C.c_size_t, _vp, _vp]),
+    "gficf_cuda_network_quality_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int32,
+                                                 C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
+    "gficf_cuda_network_reduce_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int32,
+                                                C.c_double, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp,
+                                                C.POINTER(C.c_int64), _vp, C.c_size_t, _vp, _vp]),
     "gficf_cuda_wmu_test": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_char_p, C.c_size_t]),
     "gficf_cuda_set_launch_ctas_per_sm": (C.c_int, [C.c_int32]),
     "gficf_cuda_last_launch": (C.c_int, [C.POINTER(C.c_int32)] * 4),

@@ -1967,27 +1967,29 @@ int gficf_cuda_network_dev(const int64_t* d_colptr, const int32_t* d_row, const 
 }
 
 int gficf_cuda_network_quality_dev(const int64_t* d_first, const int32_t* d_neighbor, const double* d_edge_w,
-                                   const double* d_node_w, int64_t n_nodes, const int32_t* d_cluster,
-                                   int32_t n_clusters, double resolution, double self_links,
-                                   const double* d_total_w, double* d_cluster_w, double* d_quality,
-                                   void* d_scratch, size_t scratch_bytes, uint32_t* d_flags, void* stream) {
+                                   const double* d_node_w, int64_t n_nodes, int64_t n_edges,
+                                   const int32_t* d_cluster, int32_t n_clusters, double resolution,
+                                   double self_links, const double* d_total_w, double* d_cluster_w,
+                                   double* d_quality, void* d_scratch, size_t scratch_bytes, uint32_t* d_flags,
+                                   void* stream) {
   DEV_BEGIN
-  return net_entry_quality(d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, d_cluster, n_clusters, resolution,
-                           self_links, d_total_w, d_cluster_w, d_quality, d_scratch, scratch_bytes, d_flags,
-                           (cudaStream_t)stream, sm_count() * 8);
+  return net_entry_quality(d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, n_edges, d_cluster, n_clusters,
+                           resolution, self_links, d_total_w, d_cluster_w, d_quality, d_scratch, scratch_bytes,
+                           d_flags, (cudaStream_t)stream, sm_count() * 8);
   DEV_END
 }
 
 int gficf_cuda_network_reduce_dev(const int64_t* d_first, const int32_t* d_neighbor, const double* d_edge_w,
                                   const double* d_node_w, int64_t n_nodes, int64_t n_edges,
-                                  const int32_t* d_cluster, int32_t n_clusters, int64_t* d_r_first,
-                                  int32_t* d_r_neighbor, double* d_r_edge_w, int64_t r_cap, double* d_r_node_w,
-                                  double* d_r_self_add, double* d_r_total_w, int64_t* n_reduced_edges,
-                                  void* d_scratch, size_t scratch_bytes, uint32_t* d_flags, void* stream) {
+                                  const int32_t* d_cluster, int32_t n_clusters, double self_links,
+                                  int64_t* d_r_first, int32_t* d_r_neighbor, double* d_r_edge_w, int64_t r_cap,
+                                  double* d_r_node_w, double* d_r_self_links, double* d_r_total_w,
+                                  int64_t* n_reduced_edges, void* d_scratch, size_t scratch_bytes,
+                                  uint32_t* d_flags, void* stream) {
   DEV_BEGIN
-  return net_entry_reduce(d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, n_edges, d_cluster, n_clusters, d_r_first,
-                          d_r_neighbor, d_r_edge_w, r_cap, d_r_node_w, d_r_self_add, d_r_total_w, n_reduced_edges,
-                          d_scratch, scratch_bytes, d_flags, (cudaStream_t)stream, sm_count() * 8);
+  return net_entry_reduce(d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, n_edges, d_cluster, n_clusters, self_links,
+                          d_r_first, d_r_neighbor, d_r_edge_w, r_cap, d_r_node_w, d_r_self_links, d_r_total_w,
+                          n_reduced_edges, d_scratch, scratch_bytes, d_flags, (cudaStream_t)stream, sm_count() * 8);
   DEV_END
 }
 

@@ -20,12 +20,11 @@
 //     fetches the list in parallel and replays the additions in list order): node weights (the node's
 //     neighbour list), cluster weights / reduced node weights (the cluster's nodes ascending),
 //     reduced edge weights (the cross edges of one cluster pair in traversal order) -- bit-identical;
-//   * the three sums the reference forms sequentially over the WHOLE edge list (total edge weight,
-//     the intra-cluster weight inside calcQualityFunction, the self-link total of the reduced
-//     network) and the sum over clusters of weight^2 are formed by a fixed-shape tree here
-//     (deterministic: the shape depends on the element count only), so they agree with the
-//     reference to rounding of the summation order, not bit for bit.  Tests hold them to 1e-12
-//     relative.
+//   * the sums the reference forms sequentially over the WHOLE edge list (total edge weight, the
+//     intra-cluster weight inside calcQualityFunction, the self-link total of the reduced network)
+//     are replayed exactly as well -- see "The reference's whole-graph sums, bit for bit" below --
+//     and the subtraction chain over the clusters in calcQualityFunction is done by one thread.
+//   Every double these kernels produce is the reference's double.
 //
 // Ordering primitive: a stable least-significant-digit radix sort over 64-bit keys with a 32-bit
 // payload (8-bit digits; per-tile digit histograms, one exclusive scan over (digit, tile), ranked
@@ -123,45 +122,251 @@ radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, const unsig
 }
 
 // ---------------------------------------------------------------------------------------------
-// deterministic sums of doubles: a fixed tree whose shape depends on the element count only
+// The reference's whole-graph sums, bit for bit.  std::accumulate over 10^8 doubles is a chain
+// s <- RN(s + x[t]); re-associating it changes the bits (with the few distinct Jaccard weights the
+// sequential sum drifts ~n * 2^-53 away from the true sum, 4e-10 at 5e7 terms -- measured).  But
+// the chain has structure: while s stays inside one binade [2^e, 2^(e+1)) its spacing is
+// ulp = 2^(e-52), s = S * ulp with an integer S, and for x = W * ulp + r (0 <= r < ulp)
+//     RN(s + x) = (S + W + c) * ulp,   c = [r > ulp/2], or on a tie (r == ulp/2) the choice that
+//                                          makes S + W + c even,
+// as long as S + W + c <= 2^53.  So inside a binade every element is an INTEGER increment that
+// depends on S only through its parity (ties): a pair (d_even, d_odd).  Such pairs compose
+// associatively, hence a block of elements collapses to one pair, blocks are combined in order, and
+// the increments are non-negative, so "the first element that leaves the binade" is found by
+// walking the block pairs.  That one element is added with a real floating-point add, the binade
+// changes, and the walk goes on.  The doubles produced are exactly the sequential chain's.
+//   domain: x[t] >= 0 (0 = skipped element), finite; anything else raises kFlagNetWeight.
+// A window of up to 1024 blocks x 4096 elements is processed per step; the window grows while no
+// binade boundary is met.  State lives on the device; the host only reads the position back
+// every few dozen steps.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSumThreads = 256;
-constexpr int kSumChunk = 4096;      // elements per CTA of the first level
-constexpr int kSumMaxBlocks = 1024;  // first-level CTAs are capped: chunks grow beyond 4M elements
+struct SeqFn {
+  unsigned long long d0, d1;  // increment of S when S is even / odd; saturates at kSeqClamp
+};
+struct SeqState {
+  long long t0;          // next element
+  unsigned long long S;  // s = S * 2^(e-52); S == 0 <=> s == 0
+  int e;
+  int win_blocks;        // blocks in the next window
+  double value;          // s as a double (kept for the caller)
+};
+constexpr unsigned long long kSeqClamp = 1ull << 54;
+constexpr unsigned long long kSeqTop = 1ull << 53;
+constexpr int kSeqThreads = 256;
+constexpr int kSeqPerThread = 16;
+constexpr int kSeqBlock = kSeqThreads * kSeqPerThread;  // 4096 elements
+constexpr int kSeqMaxBlocks = 1024;
 
-__device__ __forceinline__ double block_sum_256(double v, double* s_warp) {
-  for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+__device__ __forceinline__ void seq_split(double v, unsigned long long* S, int* e) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const int ef = (int)((b >> 52) & 0x7ffu);
+  const unsigned long long m = b & ((1ull << 52) - 1ull);
+  if (ef == 0) {
+    *S = m;
+    *e = -1022;
+  } else {
+    *S = m | (1ull << 52);
+    *e = ef - 1023;
+  }
+}
+
+__device__ __forceinline__ double seq_value(unsigned long long S, int e) {
+  if (S == 0) return 0.0;
+  if (S >> 52) return __longlong_as_double((long long)(((unsigned long long)(e + 1023) << 52) | (S & ((1ull << 52) - 1ull))));
+  return __longlong_as_double((long long)S);  // subnormal: e == -1022, no implicit bit
+}
+
+// the increment pair of element x while s sits in binade e
+__device__ __forceinline__ SeqFn seq_fn(double x, int e, bool* bad) {
+  SeqFn f;
+  f.d0 = f.d1 = 0;
+  if (x == 0.0) return f;
+  if (!(x > 0.0) || x > 1.7976931348623157e308) {
+    *bad = true;
+    return f;
+  }
+  unsigned long long M;
+  int ex;
+  seq_split(x, &M, &ex);
+  const int shift = e - ex;  // x = M * 2^(ex-52), ulp = 2^(e-52): x / ulp = M / 2^shift
+  if (shift <= 0) {
+    f.d0 = f.d1 = kSeqClamp;  // x alone reaches the top of the binade
+  } else if (shift <= 53) {
+    const unsigned long long W = M >> shift;
+    const unsigned long long rem = M & ((1ull << shift) - 1ull);
+    const unsigned long long half = 1ull << (shift - 1);
+    if (rem == half) {
+      f.d0 = W + (W & 1ull);
+      f.d1 = W + ((W & 1ull) ^ 1ull);
+    } else {
+      f.d0 = f.d1 = W + (rem > half ? 1ull : 0ull);
+    }
+  }  // shift >= 54: x is below half an ulp, s absorbs it
+  return f;
+}
+
+__device__ __forceinline__ unsigned long long seq_apply(unsigned long long S, SeqFn f) {
+  const unsigned long long r = S + ((S & 1ull) ? f.d1 : f.d0);
+  return r < kSeqClamp ? r : kSeqClamp;
+}
+
+// f first, then g
+__device__ __forceinline__ SeqFn seq_compose(SeqFn f, SeqFn g) {
+  SeqFn r;
+  r.d0 = f.d0 >= kSeqClamp ? kSeqClamp : seq_apply(f.d0, g);          // S even: S + d0 has the parity of d0
+  r.d1 = f.d1 >= kSeqClamp ? kSeqClamp : seq_apply(f.d1 + 1ull, g) - 1ull;  // S odd: S + d1 has the parity of d1 + 1
+  return r;
+}
+
+// the pair of elements [lo, lo + 16) (clipped at n), composed in order
+__device__ __forceinline__ SeqFn seq_thread_fn(const double* __restrict__ x, long long lo, long long n, int e,
+                                               bool* bad) {
+  SeqFn f;
+  f.d0 = f.d1 = 0;
+  for (int q = 0; q < kSeqPerThread; ++q) {
+    const long long i = lo + q;
+    if (i < n) f = seq_compose(f, seq_fn(x[i], e, bad));
+  }
+  return f;
+}
+
+__global__ void __launch_bounds__(32)
+seq_init_kernel(SeqState* __restrict__ st, double s0) {
+  if (threadIdx.x == 0) {
+    st->t0 = 0;
+    seq_split(s0, &st->S, &st->e);
+    st->win_blocks = 1;
+    st->value = s0;
+  }
+}
+
+// block_fn[b] = composition of the elements of block b of the current window
+__global__ void __launch_bounds__(kSeqThreads)
+seq_blocks_kernel(const double* __restrict__ x, long long n, const SeqState* __restrict__ st,
+                  SeqFn* __restrict__ block_fn, unsigned* __restrict__ flags) {
+  __shared__ SeqFn s_warp[kSeqThreads / 32];
+  const long long t0 = st->t0;
+  if (t0 >= n || st->S == 0) return;  // finished, or s == 0: the next element is added by seq_advance_kernel
+  const int nb = st->win_blocks, e = st->e;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool bad = false;
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    const long long lo = t0 + (long long)b * kSeqBlock + (long long)threadIdx.x * kSeqPerThread;
+    SeqFn f = seq_thread_fn(x, lo, n, e, &bad);
+    for (int off = 1; off < 32; off <<= 1) {  // ordered tree: lane i absorbs lane i + off
+      SeqFn o;
+      o.d0 = __shfl_down_sync(kFull, f.d0, off);
+      o.d1 = __shfl_down_sync(kFull, f.d1, off);
+      if ((lane & (2 * off - 1)) == 0) f = seq_compose(f, o);
+    }
+    if (lane == 0) s_warp[warp] = f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      SeqFn a = s_warp[0];
+      for (int w = 1; w < kSeqThreads / 32; ++w) a = seq_compose(a, s_warp[w]);
+      block_fn[b] = a;
+    }
+    __syncthreads();
+  }
+  if (bad) atomicOr(flags, kFlagNetWeight);
+}
+
+// one CTA: walks the block pairs of the window; either the whole window stays inside the binade
+// (s moves to its end) or the first block / thread / element that leaves it is located, that
+// element is added in floating point and the state continues behind it.  When the last element
+// is consumed, out[0] = s * scale.
+__global__ void __launch_bounds__(kSeqThreads)
+seq_advance_kernel(const double* __restrict__ x, long long n, SeqState* __restrict__ st,
+                   const SeqFn* __restrict__ block_fn, double scale, double* __restrict__ out,
+                   unsigned* __restrict__ flags) {
+  __shared__ SeqFn s_fn[kSeqMaxBlocks];
+  __shared__ int s_bstar;
+  __shared__ unsigned long long s_S;
+  // every thread takes its copy of the state before thread 0 may change it
+  const long long t0 = st->t0;
+  const unsigned long long S0 = st->S;
+  const int e = st->e;
+  const int nb = st->win_blocks;
   __syncthreads();
-  double t = 0.0;
-  if (threadIdx.x < 32) {
-    t = threadIdx.x < kSumThreads / 32 ? s_warp[threadIdx.x] : 0.0;
-    for (int m = 16; m; m >>= 1) t += __shfl_xor_sync(kFull, t, m);
+  if (t0 >= n) {
+    if (threadIdx.x == 0 && n == 0) out[0] = st->value * scale;
+    return;
+  }
+  bool bad = false;
+  if (S0 == 0) {  // s == 0: 0.0 + x is x itself
+    if (threadIdx.x == 0) {
+      const double v = x[t0];
+      if (v > 0.0 && v <= 1.7976931348623157e308) {
+        seq_split(v, &st->S, &st->e);
+        st->value = v;
+      } else if (v != 0.0) {
+        atomicOr(flags, kFlagNetWeight);
+      }
+      st->t0 = t0 + 1;
+      if (t0 + 1 >= n) out[0] = st->value * scale;
+    }
+    return;
+  }
+  for (int b = threadIdx.x; b < nb; b += kSeqThreads) s_fn[b] = block_fn[b];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long S = S0;
+    int bstar = -1;
+    for (int b = 0; b < nb; ++b) {
+      const unsigned long long nS = seq_apply(S, s_fn[b]);
+      if (nS >= kSeqTop) {
+        bstar = b;
+        break;
+      }
+      S = nS;
+    }
+    s_bstar = bstar;
+    s_S = S;  // s at the start of block bstar, or at the end of the window
   }
   __syncthreads();
-  return t;  // valid in thread 0
-}
-
-// partials[b] = sum of x[b*chunk, (b+1)*chunk); thread t adds elements t, t+256, ... of the chunk in order
-__global__ void __launch_bounds__(kSumThreads)
-sum_partials_kernel(const double* __restrict__ x, long long n, long long chunk, double* __restrict__ partials) {
-  __shared__ double s_warp[kSumThreads / 32];
-  const long long lo = (long long)blockIdx.x * chunk;
-  const long long hi = lo + chunk < n ? lo + chunk : n;
-  double v = 0.0;
-  for (long long i = lo + threadIdx.x; i < hi; i += kSumThreads) v += x[i];
-  const double t = block_sum_256(v, s_warp);
-  if (threadIdx.x == 0) partials[blockIdx.x] = t;
-}
-
-// out[0] = scale * sum of the partials (one CTA)
-__global__ void __launch_bounds__(kSumThreads)
-sum_final_kernel(const double* __restrict__ partials, int n_partials, double scale, double* __restrict__ out) {
-  __shared__ double s_warp[kSumThreads / 32];
-  double v = 0.0;
-  for (int i = threadIdx.x; i < n_partials; i += kSumThreads) v += partials[i];
-  const double t = block_sum_256(v, s_warp);
-  if (threadIdx.x == 0) out[0] = t * scale;
+  const int bstar = s_bstar;
+  if (bstar < 0) {
+    if (threadIdx.x == 0) {
+      long long end = t0 + (long long)nb * kSeqBlock;
+      if (end > n) end = n;
+      st->S = s_S;
+      st->value = seq_value(s_S, e);
+      st->t0 = end;
+      st->win_blocks = 2 * nb < kSeqMaxBlocks ? 2 * nb : kSeqMaxBlocks;
+      if (end >= n) out[0] = st->value * scale;
+    }
+    return;
+  }
+  // the crossing is inside block bstar: per-thread pairs, then thread 0 walks threads and elements
+  const long long blo = t0 + (long long)bstar * kSeqBlock;
+  __syncthreads();
+  s_fn[threadIdx.x] = seq_thread_fn(x, blo + (long long)threadIdx.x * kSeqPerThread, n, e, &bad);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long S = s_S;
+    int j = 0;
+    for (; j < kSeqThreads; ++j) {
+      const unsigned long long nS = seq_apply(S, s_fn[j]);
+      if (nS >= kSeqTop) break;
+      S = nS;
+    }
+    long long i = blo + (long long)j * kSeqPerThread;
+    for (; i < n - 1; ++i) {  // the crossing element exists: the block's pair said so (n - 1 bounds the walk regardless)
+      const unsigned long long nS = seq_apply(S, seq_fn(x[i], e, &bad));
+      if (nS >= kSeqTop) break;
+      S = nS;
+    }
+    if (i >= n) i = n - 1;  // unreachable with consistent pairs; keeps the read inside the array
+    const double s_new = __dadd_rn(seq_value(S, e), x[i]);  // the one real addition of this step
+    seq_split(s_new, &st->S, &st->e);
+    st->value = s_new;
+    st->t0 = i + 1;
+    // the next binade is twice as wide: about twice as many elements fit
+    long long want = 2 * ((i + 1 - t0) / kSeqBlock + 1);
+    st->win_blocks = want < kSeqMaxBlocks ? (int)want : kSeqMaxBlocks;
+    if (i + 1 >= n) out[0] = s_new * scale;
+  }
+  if (bad) atomicOr(flags, kFlagNetWeight);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -321,51 +526,44 @@ net_cluster_weight_kernel(const long long* __restrict__ cptr, const unsigned* __
   }
 }
 
-// intra[v] = weight of v's edges that stay inside v's cluster, added in list order (:467-469 /
-// the self-link branch :351).  Warp per node.
+// y[m] = edge weight m if both ends share a cluster, else 0 (a skipped element of the sequential sum
+// :465-469).  Warp per node, CSR order.
 __global__ void __launch_bounds__(256)
-net_intra_kernel(const long long* __restrict__ first, const int* __restrict__ neighbor,
-                 const double* __restrict__ edge_w, const int* __restrict__ cluster, long long n_nodes,
-                 double* __restrict__ intra) {
+net_intra_mask_kernel(const long long* __restrict__ first, const int* __restrict__ neighbor,
+                      const double* __restrict__ edge_w, const int* __restrict__ cluster, long long n_nodes,
+                      double* __restrict__ y) {
   const int lane = threadIdx.x & 31;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long v = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < n_nodes; v += nwarps) {
     const int c = cluster[v];
-    const double s = warp_ordered_sum(first[v], first[v + 1], lane, [&](long long m, double* x) {
-      *x = edge_w[m];
-      return cluster[neighbor[m]] == c;
-    });
-    if (lane == 0) intra[v] = s;
+    for (long long m = first[v] + lane; m < first[v + 1]; m += 32)
+      y[m] = cluster[neighbor[m]] == c ? edge_w[m] : 0.0;
   }
 }
 
-// Q = (intra + selfLinks - sum_c term[c]) / (2 * totalEdgeWeight + selfLinks)   (:470-481)
+// :470-481 in the reference's order: q = intra; q += selfLinks; q -= term[c] for c = 0, 1, ...;
+// q /= 2 * totalEdgeWeight + selfLinks.  One thread: the subtractions are a chain over the clusters.
 __global__ void __launch_bounds__(32)
-net_quality_final_kernel(const double* __restrict__ intra_sum, const double* __restrict__ term_sum,
+net_quality_final_kernel(const double* __restrict__ intra_sum, const double* __restrict__ term, int n_clusters,
                          const double* __restrict__ total_edge_w, double self_links, double* __restrict__ q) {
   if (threadIdx.x == 0) {
-    const double num = __dadd_rn(__dadd_rn(intra_sum[0], self_links), -term_sum[0]);
-    const double den = __dadd_rn(__dmul_rn(2.0, total_edge_w[0]), self_links);
-    q[0] = __ddiv_rn(num, den);
+    double v = __dadd_rn(intra_sum[0], self_links);
+    for (int c = 0; c < n_clusters; ++c) v = __dadd_rn(v, -term[c]);
+    q[0] = __ddiv_rn(v, __dadd_rn(__dmul_rn(2.0, total_edge_w[0]), self_links));
   }
 }
 
-// warp per position t of the cluster-sorted node list: cross edges of the node, weight that stays inside
+// warp per position t of the cluster-sorted node list: cross edges of the node, and its degree
 __global__ void __launch_bounds__(256)
 rn_count_kernel(const long long* __restrict__ first, const int* __restrict__ neighbor,
-                const double* __restrict__ edge_w, const int* __restrict__ cluster,
-                const unsigned* __restrict__ nodes_sorted, long long n_nodes, int* __restrict__ xcnt,
-                double* __restrict__ intra_t) {
+                const int* __restrict__ cluster, const unsigned* __restrict__ nodes_sorted, long long n_nodes,
+                int* __restrict__ xcnt, int* __restrict__ deg_t) {
   const int lane = threadIdx.x & 31;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_nodes; t += nwarps) {
     const unsigned l = nodes_sorted[t];
     const int i = cluster[l];
     const long long lo = first[l], hi = first[l + 1];
-    const double s = warp_ordered_sum(lo, hi, lane, [&](long long m, double* x) {
-      *x = edge_w[m];
-      return cluster[neighbor[m]] == i;
-    });
     int cross = 0;
     for (long long base = lo; base < hi; base += 32) {
       const long long m = base + lane;
@@ -373,8 +571,26 @@ rn_count_kernel(const long long* __restrict__ first, const int* __restrict__ nei
     }
     if (lane == 0) {
       xcnt[t] = cross;
-      intra_t[t] = s;
+      deg_t[t] = (int)(hi - lo);
     }
+  }
+}
+
+// y[gbase[t] + j] = weight of the j-th edge of node t (traversal order) if it stays inside the
+// cluster, else 0: the sequence :351 adds to totalEdgeWeightSelfLinks
+__global__ void __launch_bounds__(256)
+rn_intra_mask_kernel(const long long* __restrict__ first, const int* __restrict__ neighbor,
+                     const double* __restrict__ edge_w, const int* __restrict__ cluster,
+                     const unsigned* __restrict__ nodes_sorted, const long long* __restrict__ gbase,
+                     long long n_nodes, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_nodes; t += nwarps) {
+    const unsigned l = nodes_sorted[t];
+    const int i = cluster[l];
+    const long long lo = first[l], g = gbase[t];
+    for (long long m = lo + lane; m < first[l + 1]; m += 32)
+      y[g + (m - lo)] = cluster[neighbor[m]] == i ? edge_w[m] : 0.0;
   }
 }
 

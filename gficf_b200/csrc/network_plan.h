@@ -63,8 +63,11 @@ struct NetScratch {
   int* cnt;
   long long *ptr_a, *ptr_b;
   double *dbl_a, *dbl_b;
-  double* partials;
-  double* sums;  // [0] intra weight  [1] sum of cluster terms
+  SeqState* seq_state;
+  SeqFn* seq_fn;
+  double* sums;  // [0] intra-cluster weight of calcQualityFunction
+  long long* ptr_c;
+  int* cnt_b;
   long long n_tiles_cap;
   size_t bytes;
 };
@@ -99,8 +102,11 @@ inline NetScratch net_scratch_layout(char* base, long long nn, long long cap) {
   s.ptr_b = (long long*)take((size_t)(nn + 1) * 8);
   s.dbl_a = (double*)take((size_t)(nn + 1) * 8);
   s.dbl_b = (double*)take((size_t)(nn + 1) * 8);
-  s.partials = (double*)take((size_t)kSumMaxBlocks * 8);
+  s.seq_state = (SeqState*)take(sizeof(SeqState));
+  s.seq_fn = (SeqFn*)take((size_t)kSeqMaxBlocks * sizeof(SeqFn));
   s.sums = (double*)take(64);
+  s.ptr_c = (long long*)take((size_t)(nn + 1) * 8);
+  s.cnt_b = (int*)take((size_t)(nn + 1) * 4);
   s.bytes = off;
   return s;
 }
@@ -155,15 +161,28 @@ inline int net_radix_sort(const NetCtx& cx, int start, long long n, int nbits) {
   return cur;
 }
 
-// out[0] = scale * (x[0] + ... + x[n-1]) by the fixed tree
-inline void net_sum(const NetCtx& cx, const double* x, long long n, double scale, double* out) {
-  long long blocks = (n + kSumChunk - 1) / kSumChunk;
-  if (blocks < 1) blocks = 1;
-  if (blocks > kSumMaxBlocks) blocks = kSumMaxBlocks;
-  const long long chunk = (n + blocks - 1) / blocks;
-  double* partials = cx.sc.partials;
-  GFICF_LAUNCH(cx.st, sum_partials_kernel, blocks, kSumThreads, x, n, chunk, partials);
-  GFICF_LAUNCH(cx.st, sum_final_kernel, 1, kSumThreads, (const double*)partials, (int)blocks, scale, out);
+// out[0] = scale * (((s0 + x[0]) + x[1]) + ... + x[n-1]), every addition rounded like the sequential
+// loop rounds it (network_kernels.cuh, "The reference's whole-graph sums, bit for bit").  x >= 0.
+// Synchronises the stream (the position is read back every kSeqBatch steps).
+#ifdef GFICF_CUDA_EMU
+constexpr int kSeqBatch = 2;
+#else
+constexpr int kSeqBatch = 24;
+#endif
+inline void net_seq_sum(const NetCtx& cx, const double* x, long long n, double s0, double scale, double* out) {
+  SeqState* st = cx.sc.seq_state;
+  SeqFn* bf = cx.sc.seq_fn;
+  unsigned* flags = cx.flags;
+  const long long grid = cx.max_ctas < kSeqMaxBlocks ? cx.max_ctas : kSeqMaxBlocks;
+  GFICF_LAUNCH(cx.st, seq_init_kernel, 1, 32, st, s0);
+  long long t0 = 0;
+  do {
+    for (int it = 0; it < kSeqBatch; ++it) {
+      GFICF_LAUNCH(cx.st, seq_blocks_kernel, grid, kSeqThreads, x, n, (const SeqState*)st, bf, flags);
+      GFICF_LAUNCH(cx.st, seq_advance_kernel, 1, kSeqThreads, x, n, st, (const SeqFn*)bf, scale, out, flags);
+    }
+    net_read(cx.st, &t0, &st->t0, 8);
+  } while (t0 < n);
 }
 
 // Clustering::getNodesPerCluster (:106-118): sc.perm = nodes grouped by cluster, ascending inside
@@ -197,44 +216,49 @@ inline void net_build(const NetCtx& cx, const long long* colptr, const int* row,
                neighbor, edge_w);
   GFICF_LAUNCH(cx.st, net_node_weight_kernel, net_grid(cx, nv * 32, 256), 256, (const long long*)first,
                (const double*)edge_w, nv, node_w, cx.flags);
-  net_sum(cx, edge_w, 2 * nnz, 0.5, total_w);
+  net_seq_sum(cx, edge_w, 2 * nnz, 0.0, 0.5, total_w);
 }
 
-// calcQualityFunction.  cluster_w[n_clusters] and q[1] are outputs.
+// calcQualityFunction.  cluster_w[n_clusters] and q[1] are outputs.  Needs item capacity n_edges.
 inline void net_quality(const NetCtx& cx, const long long* first, const int* neighbor, const double* edge_w,
-                        const double* node_w, long long n_nodes, const int* cluster, int n_clusters,
-                        double resolution, double self_links, const double* total_w, double* cluster_w,
-                        double* q) {
+                        const double* node_w, long long n_nodes, long long n_edges, const int* cluster,
+                        int n_clusters, double resolution, double self_links, const double* total_w,
+                        double* cluster_w, double* q) {
   const NetScratch& sc = cx.sc;
-  GFICF_LAUNCH(cx.st, net_intra_kernel, net_grid(cx, n_nodes * 32, 256), 256, first, neighbor, edge_w, cluster,
-               n_nodes, sc.dbl_a);
-  net_sum(cx, sc.dbl_a, n_nodes, 1.0, sc.sums + 0);
+  double* y = sc.seg_w;
+  GFICF_LAUNCH(cx.st, net_intra_mask_kernel, net_grid(cx, n_nodes * 32, 256), 256, first, neighbor, edge_w, cluster,
+               n_nodes, y);
+  net_seq_sum(cx, y, n_edges, 0.0, 1.0, sc.sums + 0);
   net_nodes_per_cluster(cx, cluster, n_nodes, n_clusters);
   GFICF_LAUNCH(cx.st, net_cluster_weight_kernel, net_grid(cx, (long long)n_clusters * 32, 256), 256, (const long long*)sc.ptr_a,
                (const unsigned*)sc.perm, node_w, n_clusters, resolution, cluster_w, sc.dbl_b);
-  net_sum(cx, sc.dbl_b, n_clusters, 1.0, sc.sums + 1);
-  GFICF_LAUNCH(cx.st, net_quality_final_kernel, 1, 32, (const double*)(sc.sums + 0),
-               (const double*)(sc.sums + 1), total_w, self_links, q);
+  GFICF_LAUNCH(cx.st, net_quality_final_kernel, 1, 32, (const double*)(sc.sums + 0), (const double*)sc.dbl_b,
+               n_clusters, total_w, self_links, q);
 }
 
 // createReducedNetwork.  Outputs: r_first[n_clusters+1], r_neighbor / r_edge_w (capacity r_cap
-// entries), r_node_w[n_clusters], r_self_add[1] = the weight that moves into self links (the
-// caller adds the parent's own total, :329/:351), r_total_w[1] = getTotalEdgeWeight of the reduced
-// network.  Returns the number of reduced edges, or -1 when
-// r_cap is too small (*n_needed then holds the number).  Synchronises the stream twice to read
-// two entry counts.
+// entries), r_node_w[n_clusters], r_self_links[1] = totalEdgeWeightSelfLinks of the reduced network
+// (the parent's value `self_links` plus, in traversal order, every edge that stays inside a cluster,
+// :329/:351), r_total_w[1] = getTotalEdgeWeight of the reduced network.  Returns the number of
+// reduced edges, or -1 when
+// r_cap is too small (*n_needed then holds the number).  Synchronises the stream (entry counts and
+// the sequential sums are read back).
 inline long long net_reduce(const NetCtx& cx, const long long* first, const int* neighbor, const double* edge_w,
-                            const double* node_w, long long n_nodes, const int* cluster, int n_clusters,
-                            long long* r_first, int* r_neighbor, double* r_edge_w, long long r_cap,
-                            double* r_node_w, double* r_self_add, double* r_total_w, long long* n_needed) {
+                            const double* node_w, long long n_nodes, long long n_edges, const int* cluster,
+                            int n_clusters, double self_links, long long* r_first, int* r_neighbor,
+                            double* r_edge_w, long long r_cap, double* r_node_w, double* r_self_links,
+                            double* r_total_w, long long* n_needed) {
   const NetScratch& sc = cx.sc;
   net_nodes_per_cluster(cx, cluster, n_nodes, n_clusters);
   GFICF_LAUNCH(cx.st, net_cluster_weight_kernel, net_grid(cx, (long long)n_clusters * 32, 256), 256, (const long long*)sc.ptr_a,
                (const unsigned*)sc.perm, node_w, n_clusters, 0.0, r_node_w, (double*)nullptr);
-  GFICF_LAUNCH(cx.st, rn_count_kernel, net_grid(cx, n_nodes * 32, 256), 256, first, neighbor, edge_w, cluster,
-               (const unsigned*)sc.perm, n_nodes, sc.cnt, sc.dbl_a);
+  GFICF_LAUNCH(cx.st, rn_count_kernel, net_grid(cx, n_nodes * 32, 256), 256, first, neighbor, cluster,
+               (const unsigned*)sc.perm, n_nodes, sc.cnt, sc.cnt_b);
   net_scan(cx, sc.cnt, n_nodes, sc.ptr_b);
-  net_sum(cx, sc.dbl_a, n_nodes, 1.0, r_self_add);
+  net_scan(cx, sc.cnt_b, n_nodes, sc.ptr_c);
+  GFICF_LAUNCH(cx.st, rn_intra_mask_kernel, net_grid(cx, n_nodes * 32, 256), 256, first, neighbor, edge_w, cluster,
+               (const unsigned*)sc.perm, (const long long*)sc.ptr_c, n_nodes, sc.seg_w);
+  net_seq_sum(cx, sc.seg_w, n_edges, self_links, 1.0, r_self_links);
   long long n_cross = 0;
   net_read(cx.st, &n_cross, sc.ptr_b + n_nodes, 8);
   *n_needed = 0;
@@ -265,7 +289,7 @@ inline long long net_reduce(const NetCtx& cx, const long long* first, const int*
   GFICF_LAUNCH(cx.st, rn_write_kernel, net_grid(cx, n_seg, 256), 256, (const unsigned*)sc.vals[b2],
                (const unsigned long long*)sc.seg_key, (const double*)sc.seg_w, n_seg, cbits, r_neighbor, r_edge_w);
   net_scan(cx, sc.cnt, n_clusters, r_first);
-  net_sum(cx, r_edge_w, n_seg, 0.5, r_total_w);
+  net_seq_sum(cx, r_edge_w, n_seg, 0.0, 0.5, r_total_w);
   return n_seg;
 }
 
@@ -301,39 +325,41 @@ inline int net_entry_network(const int64_t* d_colptr, const int32_t* d_row, cons
 }
 
 inline int net_entry_quality(const int64_t* d_first, const int32_t* d_neighbor, const double* d_edge_w,
-                             const double* d_node_w, int64_t n_nodes, const int32_t* d_cluster, int32_t n_clusters,
-                             double resolution, double self_links, const double* d_total_w, double* d_cluster_w,
+                             const double* d_node_w, int64_t n_nodes, int64_t n_edges, const int32_t* d_cluster,
+                             int32_t n_clusters, double resolution, double self_links, const double* d_total_w,
+                             double* d_cluster_w,
                              double* d_quality, void* d_scratch, size_t scratch_bytes, uint32_t* d_flags,
                              net_stream_t st, int max_ctas) {
   if (!d_first || !d_neighbor || !d_edge_w || !d_node_w || !d_cluster || !d_total_w || !d_cluster_w || !d_quality)
     return GFICF_E_ARG;
-  if (n_nodes < 1 || n_clusters < 1 || n_clusters > n_nodes) return GFICF_E_ARG;
-  if (n_nodes >= 0x7fffffffLL) return GFICF_E_LIMIT;
+  if (n_nodes < 1 || n_edges < 0 || n_clusters < 1 || n_clusters > n_nodes) return GFICF_E_ARG;
+  if (n_nodes >= 0x7fffffffLL || n_edges >= 0x7fffffffLL) return GFICF_E_LIMIT;
   NetCtx cx;
-  if (!net_make_ctx(&cx, d_scratch, scratch_bytes, n_nodes, n_nodes, d_flags, st, max_ctas)) return GFICF_E_ARG;
-  net_quality(cx, (const long long*)d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, d_cluster, n_clusters,
-              resolution, self_links, d_total_w, d_cluster_w, d_quality);
+  if (!net_make_ctx(&cx, d_scratch, scratch_bytes, n_nodes, n_edges, d_flags, st, max_ctas)) return GFICF_E_ARG;
+  net_quality(cx, (const long long*)d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, n_edges, d_cluster,
+              n_clusters, resolution, self_links, d_total_w, d_cluster_w, d_quality);
   net_check_launches();
   return GFICF_OK;
 }
 
 inline int net_entry_reduce(const int64_t* d_first, const int32_t* d_neighbor, const double* d_edge_w,
                             const double* d_node_w, int64_t n_nodes, int64_t n_edges, const int32_t* d_cluster,
-                            int32_t n_clusters, int64_t* d_r_first, int32_t* d_r_neighbor, double* d_r_edge_w,
-                            int64_t r_cap, double* d_r_node_w, double* d_r_self_add, double* d_r_total_w,
+                            int32_t n_clusters, double self_links, int64_t* d_r_first, int32_t* d_r_neighbor,
+                            double* d_r_edge_w, int64_t r_cap, double* d_r_node_w, double* d_r_self_links,
+                            double* d_r_total_w,
                             int64_t* n_reduced_edges, void* d_scratch, size_t scratch_bytes, uint32_t* d_flags,
                             net_stream_t st, int max_ctas) {
   if (!d_first || !d_neighbor || !d_edge_w || !d_node_w || !d_cluster || !d_r_first || !d_r_neighbor ||
-      !d_r_edge_w || !d_r_node_w || !d_r_self_add || !d_r_total_w || !n_reduced_edges)
+      !d_r_edge_w || !d_r_node_w || !d_r_self_links || !d_r_total_w || !n_reduced_edges)
     return GFICF_E_ARG;
   if (n_nodes < 1 || n_edges < 0 || n_clusters < 1 || n_clusters > n_nodes || r_cap < 0) return GFICF_E_ARG;
   if (n_nodes >= 0x7fffffffLL || n_edges >= 0x7fffffffLL) return GFICF_E_LIMIT;
   NetCtx cx;
   if (!net_make_ctx(&cx, d_scratch, scratch_bytes, n_nodes, n_edges, d_flags, st, max_ctas)) return GFICF_E_ARG;
   long long needed = 0;
-  const long long r = net_reduce(cx, (const long long*)d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, d_cluster,
-                                 n_clusters, (long long*)d_r_first, d_r_neighbor, d_r_edge_w, r_cap, d_r_node_w,
-                                 d_r_self_add, d_r_total_w, &needed);
+  const long long r = net_reduce(cx, (const long long*)d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, n_edges,
+                                 d_cluster, n_clusters, self_links, (long long*)d_r_first, d_r_neighbor, d_r_edge_w,
+                                 r_cap, d_r_node_w, d_r_self_links, d_r_total_w, &needed);
   net_check_launches();
   *n_reduced_edges = r < 0 ? needed : r;
   return r < 0 ? GFICF_E_LIMIT : GFICF_OK;  // r_cap too small: *n_reduced_edges holds the number needed

@@ -19,9 +19,9 @@ permutation, each move changing the state the next one reads; it stays on the ho
 (INTEGRATION.md section 8 shows where these calls sit in runLouvainAlgorithm).
 
 Every kernel is the library's own (network_kernels.cuh), called through the C ABI; torch is the
-allocator and stream provider.  Index arrays, node / cluster weights and reduced edge weights are
-bit-identical to the reference; total edge weight, quality value and self-link total come from a
-fixed-shape tree sum and agree to ~1e-15 relative (tests hold 1e-12).
+allocator and stream provider.  Every output is bit-identical to the reference, including the
+sums it forms sequentially over the whole edge list (total edge weight, quality value, self-link
+total): those are replayed exactly on the device (network_kernels.cuh).
 """
 from __future__ import annotations
 
@@ -89,11 +89,11 @@ class Network:
         cw = torch.empty((nc,), dtype=torch.float64, device=dev)
         q = torch.empty((1,), dtype=torch.float64, device=dev)
         flags = D.new_flags(dev)
-        scratch = _scratch(dev, self.n_nodes, self.n_nodes)
+        scratch = _scratch(dev, self.n_nodes, self.n_edges)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gficf_cuda_network_quality_dev(
                 self.first_neighbor_index.data_ptr(), self.neighbor.data_ptr(), self.edge_weight.data_ptr(),
-                self.node_weight.data_ptr(), self.n_nodes, cl.data_ptr(), nc, float(resolution),
+                self.node_weight.data_ptr(), self.n_nodes, self.n_edges, cl.data_ptr(), nc, float(resolution),
                 self.total_edge_weight_self_links, self._total.data_ptr(), cw.data_ptr(), q.data_ptr(),
                 scratch.data_ptr(), scratch.numel(), flags.data_ptr(), D._stream_ptr()))
         _check_flags(flags)
@@ -115,21 +115,21 @@ class Network:
         r_neighbor = torch.empty((cap,), dtype=torch.int32, device=dev)
         r_edge_w = torch.empty((cap,), dtype=torch.float64, device=dev)
         r_node_w = torch.empty((nc,), dtype=torch.float64, device=dev)
-        scalars = torch.zeros((2,), dtype=torch.float64, device=dev)  # [0] self-link weight added, [1] total
+        scalars = torch.zeros((2,), dtype=torch.float64, device=dev)  # [0] self-link total, [1] total edge weight
         flags = D.new_flags(dev)
         scratch = _scratch(dev, self.n_nodes, self.n_edges)
         n_red = C.c_int64(0)
         with torch.cuda.device(dev):
             _lib.check(L.gficf_cuda_network_reduce_dev(
                 self.first_neighbor_index.data_ptr(), self.neighbor.data_ptr(), self.edge_weight.data_ptr(),
-                self.node_weight.data_ptr(), self.n_nodes, self.n_edges, cl.data_ptr(), nc, r_first.data_ptr(),
+                self.node_weight.data_ptr(), self.n_nodes, self.n_edges, cl.data_ptr(), nc,
+                self.total_edge_weight_self_links, r_first.data_ptr(),
                 r_neighbor.data_ptr(), r_edge_w.data_ptr(), cap, r_node_w.data_ptr(), scalars.data_ptr(),
                 scalars[1:].data_ptr(), C.byref(n_red), scratch.data_ptr(), scratch.numel(), flags.data_ptr(),
                 D._stream_ptr()))
         _check_flags(flags)
         e = n_red.value
-        return Network(nc, r_first, r_neighbor[:e], r_edge_w[:e], r_node_w, scalars[1:2],
-                       self.total_edge_weight_self_links + float(scalars[0]))
+        return Network(nc, r_first, r_neighbor[:e], r_edge_w[:e], r_node_w, scalars[1:2], float(scalars[0]))
 
 
 def matrix_to_network(colptr: torch.Tensor, rows: torch.Tensor, weights: torch.Tensor) -> Network:

@@ -330,26 +330,31 @@ int gficf_cuda_wmu_test(const double* mat_x, const double* mat_y, int64_t n_gene
  *   gficf_cuda_network_dev          matrixToNetwork :761-806 + Network ctor :169-188: the lower-triangle
  *                                   CSC of gficf_cuda_snn_lower_dev (node1 = column < node2 = row, rows
  *                                   ascending) -> symmetric CSR firstNeighborIndex / neighbor / edgeWeight,
- *                                   nodeWeight (= total edge weight per node :272-284), getTotalEdgeWeight
+ *                                   nodeWeight (= total edge weight per node :272-284), and
+ *                                   *d_total_w = getTotalEdgeWeight() :268-270
  *   gficf_cuda_network_quality_dev  VOSClusteringTechnique::calcQualityFunction :462-482 for a clustering
- *                                   (cluster ids 0..n_clusters-1), plus the cluster weights it forms
+ *                                   (cluster ids 0..n_clusters-1; self_links = the network's
+ *                                   totalEdgeWeightSelfLinks), plus the cluster weights it forms
  *   gficf_cuda_network_reduce_dev   Network::createReducedNetwork :322-373 (nodes per cluster :106-118):
  *                                   one node per cluster, neighbours in the reference's order of first
- *                                   appearance, *d_r_self_add = the weight that moved into self links
- * Parity: all index arrays, node weights, cluster weights and reduced edge / node weights are
- * bit-identical to the reference (each is summed by one thread in the reference's order).  The sums the
- * reference forms sequentially over the whole edge list -- total edge weight, the quality value, the
- * self-link total -- are formed by a fixed-shape tree (deterministic; equal to the reference's to the
- * rounding of the summation order, tests hold them to 1e-12 relative).
+ *                                   appearance; *d_r_self_links = the reduced network's
+ *                                   totalEdgeWeightSelfLinks (self_links of the parent plus every edge that
+ *                                   stays inside a cluster), *d_r_total_w = its getTotalEdgeWeight()
+ * Parity: every output is bit-identical to the reference.  Per-node / per-cluster / per-cluster-pair
+ * sums are added in the reference's order by one warp; the sums the reference forms sequentially over
+ * the whole edge list (total edge weight, the intra-cluster weight of the quality function, the
+ * self-link total) are replayed exactly: inside one binade of the running sum every addition is an
+ * integer increment, which composes associatively, and the few additions that cross a binade are done
+ * in floating point (network_kernels.cuh).
  * Device pointers on the current device; d_first has n_nodes + 1 int64 entries; neighbour and cluster ids
- * are int32 (the reference's int); the directed edge count must stay below 2^31.  d_scratch:
- * gficf_cuda_network_scratch_bytes(n_nodes, n_items) bytes with n_items >= nnz (network), n_nodes
- * (quality), n_edges (reduce).  Flags raised in *d_flags (zero it first): GFICF_FLAG_NET_WEIGHT -- an
- * edge weight that is not > 0; GFICF_FLAG_NET_RANGE -- an entry that is not strictly below the
+ * are int32 (the reference's int); n_edges = d_first[n_nodes], the directed edge count, below 2^31.
+ * d_scratch: gficf_cuda_network_scratch_bytes(n_nodes, n_items) bytes with n_items >= nnz (network) or
+ * n_edges (quality, reduce).  Flags raised in *d_flags (zero it first): GFICF_FLAG_NET_WEIGHT -- an edge
+ * weight that is not > 0 and finite; GFICF_FLAG_NET_RANGE -- an entry that is not strictly below the
  * diagonal, or a row / cluster id out of range; the outputs are then unspecified.
- * network and quality are asynchronous on `stream`; reduce synchronises it (it reads two entry
- * counts back) and returns the number of reduced (directed) edges in *n_reduced_edges --
- * GFICF_E_LIMIT with the needed number there when r_cap is too small. ---- */
+ * All three synchronise `stream` (the sequential sums and two entry counts are read back while they
+ * run).  reduce returns the number of reduced (directed) edges in *n_reduced_edges -- GFICF_E_LIMIT
+ * with the needed number there when r_cap is too small. ---- */
 #define GFICF_FLAG_NET_WEIGHT 32u
 #define GFICF_FLAG_NET_RANGE 64u
 size_t gficf_cuda_network_scratch_bytes(int64_t n_nodes, int64_t n_items);
@@ -358,16 +363,18 @@ int gficf_cuda_network_dev(const int64_t* d_colptr, const int32_t* d_row, const 
                            double* d_total_w, void* d_scratch, size_t scratch_bytes, uint32_t* d_flags,
                            void* stream);
 int gficf_cuda_network_quality_dev(const int64_t* d_first, const int32_t* d_neighbor, const double* d_edge_w,
-                                   const double* d_node_w, int64_t n_nodes, const int32_t* d_cluster,
-                                   int32_t n_clusters, double resolution, double self_links,
-                                   const double* d_total_w, double* d_cluster_w, double* d_quality,
-                                   void* d_scratch, size_t scratch_bytes, uint32_t* d_flags, void* stream);
+                                   const double* d_node_w, int64_t n_nodes, int64_t n_edges,
+                                   const int32_t* d_cluster, int32_t n_clusters, double resolution,
+                                   double self_links, const double* d_total_w, double* d_cluster_w,
+                                   double* d_quality, void* d_scratch, size_t scratch_bytes, uint32_t* d_flags,
+                                   void* stream);
 int gficf_cuda_network_reduce_dev(const int64_t* d_first, const int32_t* d_neighbor, const double* d_edge_w,
                                   const double* d_node_w, int64_t n_nodes, int64_t n_edges,
-                                  const int32_t* d_cluster, int32_t n_clusters, int64_t* d_r_first,
-                                  int32_t* d_r_neighbor, double* d_r_edge_w, int64_t r_cap, double* d_r_node_w,
-                                  double* d_r_self_add, double* d_r_total_w, int64_t* n_reduced_edges,
-                                  void* d_scratch, size_t scratch_bytes, uint32_t* d_flags, void* stream);
+                                  const int32_t* d_cluster, int32_t n_clusters, double self_links,
+                                  int64_t* d_r_first, int32_t* d_r_neighbor, double* d_r_edge_w, int64_t r_cap,
+                                  double* d_r_node_w, double* d_r_self_links, double* d_r_total_w,
+                                  int64_t* n_reduced_edges, void* d_scratch, size_t scratch_bytes,
+                                  uint32_t* d_flags, void* stream);
 
 /* Caps the resident CTAs per SM of the persistent Jaccard kernels launched from THIS thread (0 = what
  * the occupancy allows: the default).  For callers that run two of them side by side on different

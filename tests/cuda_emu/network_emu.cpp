@@ -43,10 +43,12 @@ void emu_radix_sort(unsigned long long* keys, unsigned* vals, long long n, int n
   memcpy(vals, c.cx.sc.vals[b], (size_t)n * 4);
 }
 
-double emu_sum(const double* x, long long n, double scale) {
-  Ctx c(1, 1, 3);
+// ((s0 + x[0]) + x[1]) + ... replayed exactly, times scale
+double emu_seq_sum(const double* x, long long n, double s0, double scale, unsigned* flags, int max_ctas) {
+  Ctx c(1, 1, max_ctas);
   double out = -1.0;
-  net_sum(c.cx, x, n, scale, &out);
+  net_seq_sum(c.cx, x, n, s0, scale, &out);
+  *flags = c.flags;
   return out;
 }
 
@@ -62,19 +64,20 @@ unsigned emu_net_quality(const long long* first, const int* neighbor, const doub
                          long long n_nodes, const int* cluster, int n_clusters, double resolution,
                          double self_links, double total_w, double* cluster_w, double* q, int max_ctas) {
   Ctx c(n_nodes, first[n_nodes], max_ctas);
-  net_quality(c.cx, first, neighbor, edge_w, node_w, n_nodes, cluster, n_clusters, resolution, self_links,
-              &total_w, cluster_w, q);
+  net_quality(c.cx, first, neighbor, edge_w, node_w, n_nodes, first[n_nodes], cluster, n_clusters, resolution,
+              self_links, &total_w, cluster_w, q);
   return c.flags;
 }
 
 long long emu_net_reduce(const long long* first, const int* neighbor, const double* edge_w, const double* node_w,
-                         long long n_nodes, const int* cluster, int n_clusters, long long* r_first,
-                         int* r_neighbor, double* r_edge_w, long long r_cap, double* r_node_w,
-                         double* r_self_add, double* r_total_w, long long* n_needed, unsigned* flags,
+                         long long n_nodes, const int* cluster, int n_clusters, double self_links,
+                         long long* r_first, int* r_neighbor, double* r_edge_w, long long r_cap, double* r_node_w,
+                         double* r_self_links, double* r_total_w, long long* n_needed, unsigned* flags,
                          int max_ctas) {
   Ctx c(n_nodes, first[n_nodes], max_ctas);
-  const long long r = net_reduce(c.cx, first, neighbor, edge_w, node_w, n_nodes, cluster, n_clusters, r_first,
-                                 r_neighbor, r_edge_w, r_cap, r_node_w, r_self_add, r_total_w, n_needed);
+  const long long r = net_reduce(c.cx, first, neighbor, edge_w, node_w, n_nodes, first[n_nodes], cluster, n_clusters,
+                                 self_links, r_first, r_neighbor, r_edge_w, r_cap, r_node_w, r_self_links,
+                                 r_total_w, n_needed);
   *flags = c.flags;
   return r;
 }
@@ -96,23 +99,26 @@ int gficf_cuda_network_dev(const int64_t* d_colptr, const int32_t* d_row, const 
 }
 
 int gficf_cuda_network_quality_dev(const int64_t* d_first, const int32_t* d_neighbor, const double* d_edge_w,
-                                   const double* d_node_w, int64_t n_nodes, const int32_t* d_cluster,
-                                   int32_t n_clusters, double resolution, double self_links,
-                                   const double* d_total_w, double* d_cluster_w, double* d_quality,
-                                   void* d_scratch, size_t scratch_bytes, uint32_t* d_flags, void*) {
-  return net_entry_quality(d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, d_cluster, n_clusters, resolution,
-                           self_links, d_total_w, d_cluster_w, d_quality, d_scratch, scratch_bytes, d_flags, 0, 2);
+                                   const double* d_node_w, int64_t n_nodes, int64_t n_edges,
+                                   const int32_t* d_cluster, int32_t n_clusters, double resolution,
+                                   double self_links, const double* d_total_w, double* d_cluster_w,
+                                   double* d_quality, void* d_scratch, size_t scratch_bytes, uint32_t* d_flags,
+                                   void*) {
+  return net_entry_quality(d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, n_edges, d_cluster, n_clusters,
+                           resolution, self_links, d_total_w, d_cluster_w, d_quality, d_scratch, scratch_bytes,
+                           d_flags, 0, 2);
 }
 
 int gficf_cuda_network_reduce_dev(const int64_t* d_first, const int32_t* d_neighbor, const double* d_edge_w,
                                   const double* d_node_w, int64_t n_nodes, int64_t n_edges,
-                                  const int32_t* d_cluster, int32_t n_clusters, int64_t* d_r_first,
-                                  int32_t* d_r_neighbor, double* d_r_edge_w, int64_t r_cap, double* d_r_node_w,
-                                  double* d_r_self_add, double* d_r_total_w, int64_t* n_reduced_edges,
-                                  void* d_scratch, size_t scratch_bytes, uint32_t* d_flags, void*) {
-  return net_entry_reduce(d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, n_edges, d_cluster, n_clusters, d_r_first,
-                          d_r_neighbor, d_r_edge_w, r_cap, d_r_node_w, d_r_self_add, d_r_total_w, n_reduced_edges,
-                          d_scratch, scratch_bytes, d_flags, 0, 2);
+                                  const int32_t* d_cluster, int32_t n_clusters, double self_links,
+                                  int64_t* d_r_first, int32_t* d_r_neighbor, double* d_r_edge_w, int64_t r_cap,
+                                  double* d_r_node_w, double* d_r_self_links, double* d_r_total_w,
+                                  int64_t* n_reduced_edges, void* d_scratch, size_t scratch_bytes,
+                                  uint32_t* d_flags, void*) {
+  return net_entry_reduce(d_first, d_neighbor, d_edge_w, d_node_w, n_nodes, n_edges, d_cluster, n_clusters, self_links,
+                          d_r_first, d_r_neighbor, d_r_edge_w, r_cap, d_r_node_w, d_r_self_links, d_r_total_w,
+                          n_reduced_edges, d_scratch, scratch_bytes, d_flags, 0, 2);
 }
 
 }  // extern "C"

@@ -1,14 +1,12 @@
 """Shared inputs and comparisons of the network tests (emulated on the CPU, and on the GPU)."""
 import numpy as np
 
-def seq_sum_tol(n_terms):
-    """Relative distance allowed between a fixed-tree sum (error ~ log2(n) u) and the reference's
-    strictly sequential sum of n positive terms (error up to (n-1) u, u = 2^-53; with the few distinct
-    Jaccard weights the rounding errors are correlated and the sequential sum really drifts that far)."""
-    return max(n_terms, 64) * 2.0 ** -53
-
-
-REL = seq_sum_tol(1 << 22)  # cases of up to ~4M terms
+def seq_sum(x, s0=0.0):
+    """std::accumulate(first, last, s0): strictly left to right (np.cumsum on a 1-D array adds in order)."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.size == 0:
+        return float(s0)
+    return float(np.cumsum(np.concatenate([[s0], x]))[-1])
 
 
 def random_lower(rng, nv, m, k=20):
@@ -31,11 +29,12 @@ def to_csc(node1, node2, nv):
     return np.cumsum(colptr), node2.copy()
 
 
-def assert_same_network(got, want, exact_totals=False):
+def assert_same_network(got, want):
+    """Every array and every scalar bit for bit."""
     assert got["n_nodes"] == want["n_nodes"]
     assert np.array_equal(got["first"].astype(np.int64), want["first"].astype(np.int64))
     assert np.array_equal(got["neighbor"], want["neighbor"])
-    assert np.array_equal(got["edge_w"], want["edge_w"])  # bit-exact
-    assert np.array_equal(got["node_w"], want["node_w"])  # bit-exact
-    assert abs(got["self_links"] - want["self_links"]) <= REL * max(1.0, abs(want["self_links"]))
-    assert abs(got["total_w"] - want["total_w"]) <= REL * max(1.0, abs(want["total_w"]))
+    assert np.array_equal(got["edge_w"], want["edge_w"])
+    assert np.array_equal(got["node_w"], want["node_w"])
+    assert got["self_links"] == want["self_links"]
+    assert got["total_w"] == want["total_w"]

@@ -11,7 +11,7 @@ import torch
 from gficf_b200 import synth
 from oracle import louvain
 from oracle.binding import MODOPT_BIN, NetworkOracle, NetworkReference
-from tests.network_cases import REL, assert_same_network, random_lower, to_csc
+from tests.network_cases import assert_same_network, random_lower, to_csc
 
 pytestmark = pytest.mark.gpu
 
@@ -51,9 +51,7 @@ def test_network_quality_and_reduction_match_oracle(cuda, nv, m, nc, seed):
     cl = full_clustering(rng, nv, nc)
     res = 0.8 / (2 * want["total_w"])
     q_want, cw_want = O.quality(want, cl, res)
-    q = net.calc_quality_function(cl, res)
-    assert abs(q - q_want) <= REL * max(1.0, abs(q_want))
-    assert q == net.calc_quality_function(cl, res)  # fixed-shape sums: the same bits every time
+    assert net.calc_quality_function(cl, res) == q_want  # the reference's double, bit for bit
     assert np.array_equal(net.cluster_weights(cl).cpu().numpy(), cw_want)  # bit-exact
     red_want = O.reduce(want, cl)
     red = net.create_reduced_network(cl)
@@ -62,7 +60,7 @@ def test_network_quality_and_reduction_match_oracle(cuda, nv, m, nc, seed):
         nc2 = max(2, nc // 5)
         cl2 = full_clustering(rng, nc, nc2)
         q2_want, cw2_want = O.quality(red_want, cl2, res)
-        assert abs(red.calc_quality_function(cl2, res) - q2_want) <= REL * max(1.0, abs(q2_want))
+        assert red.calc_quality_function(cl2, res) == q2_want
         assert np.array_equal(red.cluster_weights(cl2).cpu().numpy(), cw2_want)
         assert_same_network(as_dict(red.create_reduced_network(cl2)), O.reduce(red_want, cl2))
 
@@ -81,7 +79,7 @@ def test_edge_cases(cuda):
     assert red.n_edges == 0
     assert_same_network(as_dict(red), O.reduce(want, one))
     q_want, _ = O.quality(want, one, 0.01)
-    assert abs(net.calc_quality_function(one, 0.01) - q_want) <= REL
+    assert net.calc_quality_function(one, 0.01) == q_want
     single = np.arange(nv, dtype=np.int32)  # singletons: the reduced network is the network
     red = as_dict(net.create_reduced_network(single))
     assert_same_network(red, O.reduce(want, single))
@@ -100,14 +98,14 @@ def test_edge_cases(cuda):
     needed = C.c_int64(0)
     rc = L.gficf_cuda_network_reduce_dev(net.first_neighbor_index.data_ptr(), net.neighbor.data_ptr(),
                                          net.edge_weight.data_ptr(), net.node_weight.data_ptr(), nv, net.n_edges,
-                                         d_cl.data_ptr(), 9, r_first.data_ptr(), r_nb.data_ptr(), r_w.data_ptr(), 3,
+                                         d_cl.data_ptr(), 9, 0.0, r_first.data_ptr(), r_nb.data_ptr(), r_w.data_ptr(), 3,
                                          r_nw.data_ptr(), sc.data_ptr(), sc[1:].data_ptr(), C.byref(needed),
                                          scratch.data_ptr(), scratch.numel(), flags.data_ptr(), 0)
     assert rc == 5 and needed.value == O.reduce(want, cl)["neighbor"].size
     # a scratch buffer that is too small is refused before anything is launched
     rc = L.gficf_cuda_network_reduce_dev(net.first_neighbor_index.data_ptr(), net.neighbor.data_ptr(),
                                          net.edge_weight.data_ptr(), net.node_weight.data_ptr(), nv, net.n_edges,
-                                         d_cl.data_ptr(), 9, r_first.data_ptr(), r_nb.data_ptr(), r_w.data_ptr(), 3,
+                                         d_cl.data_ptr(), 9, 0.0, r_first.data_ptr(), r_nb.data_ptr(), r_w.data_ptr(), 3,
                                          r_nw.data_ptr(), sc.data_ptr(), sc[1:].data_ptr(), C.byref(needed),
                                          scratch.data_ptr(), 1024, flags.data_ptr(), 0)
     assert rc == 1
@@ -157,7 +155,7 @@ def test_on_the_device_graph_of_a_knn_matrix_with_reference_labels(cuda, oracle)
     cl = labels.astype(np.int32)
     res = 0.8 / (2 * want["total_w"])  # resolution2 of RModularityOptimizer.cpp:101
     q_want, cw_want = O.quality(want, cl, res)
-    assert abs(net.calc_quality_function(cl, res) - q_want) <= REL
+    assert net.calc_quality_function(cl, res) == q_want
     assert np.array_equal(net.cluster_weights(cl).cpu().numpy(), cw_want)
     red_want = O.reduce(want, cl)
     red = net.create_reduced_network(cl)
@@ -165,7 +163,7 @@ def test_on_the_device_graph_of_a_knn_matrix_with_reference_labels(cuda, oracle)
     if NetworkReference.available():
         R = NetworkReference()
         ref_net = R.network(cols, rows_ref, data_ref)
-        assert abs(net.calc_quality_function(cl, res) - R.quality(ref_net, cl, res)) <= REL
+        assert net.calc_quality_function(cl, res) == R.quality(ref_net, cl, res)
         ref_red = R.reduce(ref_net, cl)
         assert_same_network(as_dict(red), ref_red)
         R.free(ref_red)

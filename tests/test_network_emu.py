@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from tests.network_cases import REL, assert_same_network, random_lower, to_csc
+from tests.network_cases import assert_same_network, random_lower, seq_sum, to_csc
 from oracle.binding import NetworkOracle, NetworkReference
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -32,15 +32,15 @@ def emu(tmp_path_factory):
     L = C.CDLL(so)
     L.emu_scan.argtypes = [_ip, C.c_longlong, _ll]
     L.emu_radix_sort.argtypes = [_ullp, _up, C.c_longlong, C.c_int, C.c_int]
-    L.emu_sum.argtypes = [_dp, C.c_longlong, C.c_double]
-    L.emu_sum.restype = C.c_double
+    L.emu_seq_sum.argtypes = [_dp, C.c_longlong, C.c_double, C.c_double, _up, C.c_int]
+    L.emu_seq_sum.restype = C.c_double
     L.emu_net_build.argtypes = [_ll, _ip, _dp, C.c_longlong, C.c_longlong, _ll, _ip, _dp, _dp, _dp, C.c_int]
     L.emu_net_build.restype = C.c_uint
     L.emu_net_quality.argtypes = [_ll, _ip, _dp, _dp, C.c_longlong, _ip, C.c_int, C.c_double, C.c_double,
                                   C.c_double, _dp, _dp, C.c_int]
     L.emu_net_quality.restype = C.c_uint
-    L.emu_net_reduce.argtypes = [_ll, _ip, _dp, _dp, C.c_longlong, _ip, C.c_int, _ll, _ip, _dp, C.c_longlong,
-                                 _dp, _dp, _dp, _ll, _up, C.c_int]
+    L.emu_net_reduce.argtypes = [_ll, _ip, _dp, _dp, C.c_longlong, _ip, C.c_int, C.c_double, _ll, _ip, _dp,
+                                 C.c_longlong, _dp, _dp, _dp, _ll, _up, C.c_int]
     L.emu_net_reduce.restype = C.c_longlong
     return L
 
@@ -76,19 +76,20 @@ def emu_reduce(L, net, cluster, nc, ctas=3, r_cap=None):
     r_neighbor = np.zeros(max(cap, 1), np.int32)
     r_edge_w = np.zeros(max(cap, 1), np.float64)
     r_node_w = np.zeros(nc, np.float64)
-    self_add = np.zeros(1, np.float64)
+    self_links = np.full(1, -1.0, np.float64)
     total = np.full(1, -1.0, np.float64)
     needed = np.zeros(1, np.int64)
     flags = np.zeros(1, np.uint32)
     n = L.emu_net_reduce(_p(net["first"], _ll), _p(net["neighbor"], _ip), _p(net["edge_w"], _dp),
-                         _p(net["node_w"], _dp), net["n_nodes"], _p(cl, _ip), nc, _p(r_first, _ll),
-                         _p(r_neighbor, _ip), _p(r_edge_w, _dp), cap, _p(r_node_w, _dp), _p(self_add, _dp),
+                         _p(net["node_w"], _dp), net["n_nodes"], _p(cl, _ip), nc, net["self_links"],
+                         _p(r_first, _ll), _p(r_neighbor, _ip), _p(r_edge_w, _dp), cap, _p(r_node_w, _dp),
+                         _p(self_links, _dp),
                          _p(total, _dp), _p(needed, _ll), _p(flags, _up), ctas)
     if n < 0:
         return None, int(needed[0])
     ew = r_edge_w[:n].copy()
     return dict(n_nodes=nc, first=r_first, neighbor=r_neighbor[:n].copy(), edge_w=ew, node_w=r_node_w,
-                total_w=float(total[0]), self_links=net["self_links"] + float(self_add[0])), int(flags[0])
+                total_w=float(total[0]), self_links=float(self_links[0])), int(flags[0])
 
 
 def test_emulated_scan_sort_and_sum(emu):
@@ -105,9 +106,42 @@ def test_emulated_scan_sort_and_sum(emu):
         emu.emu_radix_sort(_p(k2, _ullp), _p(v2, _up), n, nbits, ctas)
         order = np.argsort(keys, kind="stable")
         assert np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order]), (n, nbits)
-    for n in [0, 1, 255, 4097, 20000]:
-        x = rng.random(n)
-        assert abs(emu.emu_sum(_p(x, _dp), n, 0.5) - 0.5 * x.sum()) <= 1e-12 * max(1.0, x.sum())
+
+
+def _emu_seq(emu, x, s0=0.0, scale=1.0, ctas=3):
+    x = np.ascontiguousarray(x, np.float64)
+    flags = np.zeros(1, np.uint32)
+    return emu.emu_seq_sum(_p(x, _dp), x.size, s0, scale, _p(flags, _up), ctas), int(flags[0])
+
+
+def test_emulated_sequential_sum_is_the_sequential_sum(emu):
+    """The exact replay of s <- RN(s + x[t]): every case must give the bits of the left-to-right loop."""
+    rng = np.random.default_rng(3)
+    k = 30
+    cases = {
+        "empty": np.zeros(0), "one": np.array([0.3]), "zeros": np.zeros(100),
+        "jaccard weights": rng.integers(1, k + 1, 70_000) / (2 * k - rng.integers(1, k + 1, 70_000)),
+        "few distinct values (correlated rounding)": np.repeat([1 / 3, 0.1, 1 / 59, 2 / 58], 30_000),
+        "ties: powers of two and halves": rng.choice([0.5, 0.25, 1.0, 3.0, 1.5, 2.0 ** -20, 2.0 ** -30], 50_000),
+        "uniform": rng.random(40_000),
+        "wide range": np.exp(rng.normal(0, 12, 30_000)),
+        "large then tiny (absorbed)": np.concatenate([[1e18], rng.random(9000), [3e18], rng.random(5000) * 1e3]),
+        "with skipped elements": rng.random(50_000) * (rng.random(50_000) < 0.3),
+        "subnormal start": np.concatenate([[5e-324, 1e-310, 2.5e-308], rng.random(3000) * 1e-300]),
+        "one past a block": rng.random(4097), "exactly a block": rng.random(4096),
+    }
+    for name, x in cases.items():
+        for s0 in (0.0, 7.25, 1e-3):
+            got, flags = _emu_seq(emu, x, s0)
+            assert flags == 0, name
+            assert got == seq_sum(x, s0), (name, s0, got, seq_sum(x, s0))
+    x = cases["jaccard weights"]
+    assert _emu_seq(emu, x, 0.0, 0.5, ctas=1)[0] == seq_sum(x) / 2.0
+    # the domain: non-negative finite values
+    for bad in (-1.0, np.nan, np.inf):
+        y = rng.random(5000)
+        y[1234] = bad
+        assert _emu_seq(emu, y)[1] & 32
 
 
 @pytest.mark.parametrize("nv,m,nc,seed", [(5, 6, 2, 1), (60, 300, 7, 2), (700, 6000, 40, 3), (1500, 9000, 300, 4),
@@ -121,7 +155,6 @@ def test_emulated_network_pipeline_matches_oracle(emu, nv, m, nc, seed):
     got, flags = emu_build(emu, n1, n2, w, nv)
     assert flags == 0
     assert_same_network(got, want)
-    assert abs(got["total_w"] - want["total_w"]) <= REL * want["total_w"]
     # level 0: quality and reduced network for a random clustering that uses every cluster id
     nc = min(nc, nv)
     cl = rng.integers(0, nc, nv).astype(np.int32)
@@ -131,7 +164,7 @@ def test_emulated_network_pipeline_matches_oracle(emu, nv, m, nc, seed):
     q, cw, flags = emu_quality(emu, got, cl, nc, res)
     assert flags == 0
     assert np.array_equal(cw, cw_want)
-    assert abs(q - q_want) <= REL * max(1.0, abs(q_want))
+    assert q == q_want
     red_want = O.reduce(want, cl)
     red, flags = emu_reduce(emu, got, cl, nc)
     assert flags == 0
@@ -144,7 +177,7 @@ def test_emulated_network_pipeline_matches_oracle(emu, nv, m, nc, seed):
         q2_want, cw2_want = O.quality(red_want, cl2, res)
         q2, cw2, _ = emu_quality(emu, red, cl2, nc2, res)
         assert np.array_equal(cw2, cw2_want)
-        assert abs(q2 - q2_want) <= REL * max(1.0, abs(q2_want))
+        assert q2 == q2_want
         red2_want = O.reduce(red_want, cl2)
         red2, _ = emu_reduce(emu, red, cl2, nc2)
         assert_same_network(red2, red2_want)
@@ -165,7 +198,7 @@ def test_emulated_edge_cases(emu):
     assert_same_network(red, red_want)
     q, cw, _ = emu_quality(emu, got, one, 1, 0.01)
     q_want, cw_want = O.quality(want, one, 0.01)
-    assert np.array_equal(cw, cw_want) and abs(q - q_want) <= REL
+    assert np.array_equal(cw, cw_want) and q == q_want
     # singletons: the reduced network is the network itself
     single = np.arange(nv, dtype=np.int32)
     red, _ = emu_reduce(emu, got, single, nv)
@@ -205,7 +238,7 @@ def test_emulated_pipeline_matches_reference_classes(emu):
     cl[:25] = np.arange(25)
     res = 0.8 / (2 * want["total_w"])
     q, _, _ = emu_quality(emu, got, cl, 25, res)
-    assert abs(q - R.quality(want, cl, res)) <= REL
+    assert q == R.quality(want, cl, res)
     red_want = R.reduce(want, cl)
     red, _ = emu_reduce(emu, got, cl, 25)
     assert_same_network(red, red_want)
@@ -251,14 +284,14 @@ def test_python_mirror_over_the_emulated_abi(emu, monkeypatch):
     cl[:12] = np.arange(12)
     res = 0.8 / (2 * want["total_w"])
     q_want, cw_want = O.quality(want, cl, res)
-    assert abs(net.calc_quality_function(cl, res) - q_want) <= REL
+    assert net.calc_quality_function(cl, res) == q_want
     assert np.array_equal(net.cluster_weights(cl).numpy(), cw_want)
     red_want = O.reduce(want, cl)
     red = net.create_reduced_network(cl)
     assert_same_network(as_dict(red), red_want)
     cl2 = np.array([0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2], np.int32)
     q2_want, _ = O.quality(red_want, cl2, res)
-    assert abs(red.calc_quality_function(cl2, res) - q2_want) <= REL
+    assert red.calc_quality_function(cl2, res) == q2_want
     assert_same_network(as_dict(red.create_reduced_network(cl2)), O.reduce(red_want, cl2))
     # flags surface as errors
     bad = cl.copy()
@@ -297,6 +330,6 @@ def test_emulated_on_a_jaccard_graph_with_the_reference_louvain_labels(emu, orac
     res = 0.8 / (2 * want["total_w"])
     q_want, cw_want = O.quality(want, cl, res)
     q, cw, _ = emu_quality(emu, got, cl, nc, res)
-    assert np.array_equal(cw, cw_want) and abs(q - q_want) <= REL
+    assert np.array_equal(cw, cw_want) and q == q_want
     red, _ = emu_reduce(emu, got, cl, nc)
     assert_same_network(red, O.reduce(want, cl))
