@@ -8,6 +8,11 @@ oracle/_ref/libgficf_ref.so by oracle/Makefile (R runtime replaced by oracle/rsh
     python tests/golden/make_golden.py
 
 Each file holds: idx (n x k float64, 1-based), parallel (E x 3), serial (E x 3).
+wmu_*.npz: Mann-Whitney inputs and the reference worker's output (oracle/_ref/libgficf_ref_wmu.so).
+net_*.npz: a lower-triangle edge list, a clustering and a second-level clustering, with what the
+reference's own Network / VOSClusteringTechnique classes (oracle/_ref/libgficf_ref_modopt.so, built
+from src/ModularityOptimizer.cpp unmodified) make of them: the network, its quality value, the
+reduced network, and the same once more on the reduced network.
 """
 import os
 import sys
@@ -61,8 +66,52 @@ def wmu_cases():
     yield "wmu_dense_negative_10x1_40", m[:, :1], m[:, 1:]
 
 
+def net_cases():
+    from oracle import louvain
+    from gficf_b200 import synth
+    from tests.network_cases import random_lower
+
+    rng = np.random.default_rng(20261017)
+
+    def clustering(n, nc):
+        cl = rng.integers(0, nc, n).astype(np.int32)
+        cl[rng.permutation(n)[:nc]] = np.arange(nc)
+        return cl
+
+    n1, n2, w = random_lower(rng, 400, 3000)
+    yield "net_random_400_3000", n1, n2, w, clustering(int(max(n1.max(), n2.max())) + 1, 31), clustering(31, 5)
+    n1, n2, w = random_lower(rng, 64, 1500)  # dense: long neighbour lists, heavy cluster pairs
+    yield "net_dense_64_1500", n1, n2, w, clustering(int(max(n1.max(), n2.max())) + 1, 6), clustering(6, 2)
+    # the real thing: SNN graph of a planted kNN matrix, clustering = the reference's own Louvain labels
+    idx = synth.to_r_matrix(synth.knn_index(900, 12, family="planted", scramble=True))
+    rel = Reference().parallel(idx, nthreads=1)
+    names, cols, rows, data = louvain.lower_triangle_edges(rel)
+    _, labels = louvain.louvain_labels(rel, n_start=2, n_iter=3)
+    nc = int(labels.max()) + 1
+    yield "net_snn_900_k12_louvain", cols.astype(np.int32), rows.astype(np.int32), data, labels.astype(np.int32), \
+        clustering(nc, max(2, nc // 3))
+
+
 def main():
-    from oracle.binding import WmuReference
+    from oracle.binding import NetworkReference, WmuReference
+
+    nref = NetworkReference()
+    for name, n1, n2, w, cl, cl2 in net_cases():
+        net = nref.network(n1, n2, w)
+        res = 0.8 / (2 * net["total_w"] + net["self_links"])  # resolution2, RModularityOptimizer.cpp:101
+        q = nref.quality(net, cl, res)
+        red = nref.reduce(net, cl)
+        q2 = nref.quality(red, cl2, res)
+        red2 = nref.reduce(red, cl2)
+        out = dict(node1=n1, node2=n2, w=w, cluster=cl, cluster2=cl2, resolution=res, quality=q, quality2=q2)
+        for tag, x in (("net", net), ("red", red), ("red2", red2)):
+            for key in ("first", "neighbor", "edge_w", "node_w", "total_w", "self_links"):
+                out[tag + "_" + key] = x[key]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "nodes", net["n_nodes"], "edges", net["neighbor"].size, "->", red["n_nodes"], red["neighbor"].size,
+              "->", red2["n_nodes"], red2["neighbor"].size, "Q %.6f %.6f" % (q, q2))
+        for x in (red2, red, net):
+            nref.free(x)
 
     wref = WmuReference()
     for name, x, y in wmu_cases():

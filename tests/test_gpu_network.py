@@ -168,3 +168,21 @@ def test_on_the_device_graph_of_a_knn_matrix_with_reference_labels(cuda, oracle)
         assert_same_network(as_dict(red), ref_red)
         R.free(ref_red)
         R.free(ref_net)
+
+
+def test_network_golden_vectors(cuda):
+    """tests/golden/net_*.npz: outputs of the reference's own classes (make_golden.py)."""
+    from tests.test_network_oracle import NET_GOLDEN, golden_network
+
+    assert len(NET_GOLDEN) >= 3
+    for path in NET_GOLDEN:
+        g = np.load(path)
+        want = golden_network(g, "net")
+        net = gpu_network(g["node1"], g["node2"], g["w"], want["n_nodes"])
+        assert_same_network(as_dict(net), want)
+        res = float(g["resolution"])
+        assert net.calc_quality_function(g["cluster"], res) == float(g["quality"])
+        red = net.create_reduced_network(g["cluster"])
+        assert_same_network(as_dict(red), golden_network(g, "red"))
+        assert red.calc_quality_function(g["cluster2"], res) == float(g["quality2"])
+        assert_same_network(as_dict(red.create_reduced_network(g["cluster2"])), golden_network(g, "red2"))

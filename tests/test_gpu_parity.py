@@ -14,7 +14,7 @@ from tests.conftest import random_knn
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("wmu_"))  # wmu_*: Mann-Whitney fixtures (test_wmu_oracle.py)
+                if not os.path.basename(p).startswith(("wmu_", "net_")))  # other rows' fixtures: test_wmu_oracle.py, test_network_oracle.py
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

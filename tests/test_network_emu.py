@@ -333,3 +333,23 @@ def test_emulated_on_a_jaccard_graph_with_the_reference_louvain_labels(emu, orac
     assert np.array_equal(cw, cw_want) and q == q_want
     red, _ = emu_reduce(emu, got, cl, nc)
     assert_same_network(red, O.reduce(want, cl))
+
+
+def test_emulated_pipeline_matches_the_golden_vectors(emu):
+    """tests/golden/net_*.npz: outputs of the reference's own classes (make_golden.py)."""
+    from tests.test_network_oracle import NET_GOLDEN, golden_network
+
+    for path in NET_GOLDEN:
+        g = np.load(path)
+        want = golden_network(g, "net")
+        got, flags = emu_build(emu, g["node1"], g["node2"], g["w"], want["n_nodes"])
+        assert flags == 0
+        assert_same_network(got, want)
+        res, cl, cl2 = float(g["resolution"]), g["cluster"], g["cluster2"]
+        nc, nc2 = int(cl.max()) + 1, int(cl2.max()) + 1
+        assert emu_quality(emu, got, cl, nc, res)[0] == float(g["quality"])
+        red, _ = emu_reduce(emu, got, cl, nc)
+        assert_same_network(red, golden_network(g, "red"))
+        assert emu_quality(emu, red, cl2, nc2, res)[0] == float(g["quality2"])
+        red2, _ = emu_reduce(emu, red, cl2, nc2)
+        assert_same_network(red2, golden_network(g, "red2"))
