@@ -10,8 +10,10 @@ operator interface for the path:
   src/jaccard_coeff.cpp:19-45)
 * :func:`phenograph_edges`            (the call site, R/clustCells.R:63-66)
 
-plus device-resident entry points (:mod:`gficf_b200.device`) and row sharding over
-``torch.distributed`` (:mod:`gficf_b200.sharding`).  There is no CPU implementation
+plus device-resident entry points (:mod:`gficf_b200.device`), row sharding over
+``torch.distributed`` (:mod:`gficf_b200.sharding`) and the steps after the path: the graph the
+community detection reads (:mod:`gficf_b200.snn`), its network / quality / reduced-network
+steps (:mod:`gficf_b200.modularity`), Mann-Whitney U per gene (:mod:`gficf_b200.wmu`).  There is no CPU implementation
 here: every call goes to the CUDA library and fails loudly when it (or a GPU) is
 missing.
 """
