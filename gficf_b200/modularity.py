@@ -142,6 +142,8 @@ def matrix_to_network(colptr: torch.Tensor, rows: torch.Tensor, weights: torch.T
     nv, nnz = int(colptr.shape[0]) - 1, int(rows.shape[0])
     if nv < 1 or nnz < 1:
         raise ValueError("Matrix contained no network data.  Check format.")  # RModularityOptimizer.cpp:84-86
+    if 2 * nnz >= 2 ** 31 - 1:
+        raise ValueError("the network would have %d directed edges: beyond the reference's int indices" % (2 * nnz))
     dev = rows.device
     first = torch.empty((nv + 1,), dtype=torch.int64, device=dev)
     neighbor = torch.empty((2 * nnz,), dtype=torch.int32, device=dev)

@@ -116,18 +116,36 @@ def knn_index(n: int, k: int, family: str = "planted", seed: int = 180582, scram
 def scramble_ids(idx: torch.Tensor, seed: int = 180582) -> torch.Tensor:
     """Relabel cells with x -> (a*x + b) mod n: row pi(i) of the result is pi(row i of idx)."""
     n = idx.shape[0]
-    a = (0x9E3779B1 * (2 * (seed % 1000) + 1)) % n
-    if a < 2:
-        a = 1 if n <= 2 else 2
-    while math.gcd(a, n) != 1:
-        a += 1
-    b = (seed * 7919) % n
+    a, b = _scramble_coefficients(n, seed)
     rows = torch.arange(n, dtype=torch.int64, device=idx.device)
     new_pos = (rows * a + b) % n
     vals = ((idx.to(torch.int64) * a + b) % n).to(torch.int32)
     out = torch.empty_like(idx)
     out[new_pos] = vals
     return out
+
+
+def _scramble_coefficients(n: int, seed: int):
+    a = (0x9E3779B1 * (2 * (seed % 1000) + 1)) % n
+    if a < 2:
+        a = 1 if n <= 2 else 2
+    while math.gcd(a, n) != 1:
+        a += 1
+    return a, (seed * 7919) % n
+
+
+def planted_community(n: int, k: int, seed: int = 180582, scramble: bool = False, cluster: int | None = None,
+                      device="cpu") -> torch.Tensor:
+    """int32 [n]: the planted community of every cell of knn_index(n, k, family="planted", ...), in the ids
+    that call returns (the block of `cluster` consecutive ORIGINAL ids the cell belongs to)."""
+    if cluster is None:
+        cluster = 256 if k <= 30 else 1024
+    cluster = min(cluster, n)
+    ids = torch.arange(n, dtype=torch.int64, device=device)
+    if scramble:
+        a, b = _scramble_coefficients(n, seed)
+        ids = ((ids - b) % n) * pow(a, -1, n) % n  # inverse of x -> (a*x + b) mod n
+    return (ids // cluster).to(torch.int32)
 
 
 def to_r_matrix(idx0: torch.Tensor):

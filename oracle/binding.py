@@ -245,6 +245,8 @@ class NetworkOracle:
         L.modopt_quality.restype = C.c_double
         L.modopt_reduce.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _ip, C.c_int, _ip, _ip, _dp, _dp, _dp]
         L.modopt_reduce.restype = C.c_longlong
+        L.modopt_seq_sum.argtypes = [_dp, C.c_longlong, C.c_double]
+        L.modopt_seq_sum.restype = C.c_double
 
     def network(self, node1, node2, w) -> dict:
         a, b, ww = _i32(node1), _i32(node2), _f64(w)
@@ -283,16 +285,8 @@ class NetworkOracle:
                                        _ptr(node_w), C.byref(self_links))
         ew = edge_w[:n_red].copy()
         return dict(n_nodes=nc, first=first, neighbor=neighbor[:n_red].copy(), edge_w=ew, node_w=node_w,
-                    total_w=_seq_sum(ew) / 2.0,
+                    total_w=self.lib.modopt_seq_sum(_ptr(ew), ew.size, 0.0) / 2.0,
                     self_links=self_links.value)
-
-
-def _seq_sum(x: np.ndarray) -> float:
-    """std::accumulate(first, last, 0.0): strictly left to right (numpy's sum is pairwise)."""
-    s = 0.0
-    for v in x.tolist():
-        s += v
-    return s
 
 
 class NetworkReference:

@@ -57,6 +57,13 @@ long long modopt_network(const int* node1, const int* node2, const double* w, lo
   return n_edges;
 }
 
+/* std::accumulate(x, x + n, s0): what Network::getTotalEdgeWeight (:268-270) does before halving */
+double modopt_seq_sum(const double* x, long long n, double s0) {
+  long long i;
+  for (i = 0; i < n; ++i) s0 += x[i];
+  return s0;
+}
+
 /* cluster_w[n_clusters] is an output as well (the weights :474-476 forms on the way) */
 double modopt_quality(int n_nodes, const int* first, const int* neighbor, const double* edge_w,
                       const double* node_w, double self_links, double total_w, const int* cluster,

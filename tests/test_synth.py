@@ -35,3 +35,15 @@ def test_scramble_is_a_relabelling(oracle):
     rb = oracle.parallel(synth.to_r_matrix(b))
     # the multiset of weights is invariant under relabelling
     assert np.array_equal(np.sort(ra[:, 2]), np.sort(rb[:, 2]))
+
+
+def test_planted_community_follows_the_scramble():
+    """The label of a cell is the block of its ORIGINAL id: ~95 % of the neighbours share it, with or
+    without the id scramble."""
+    n, k = 20_000, 15
+    for scramble in (False, True):
+        idx = synth.knn_index(n, k, family="planted", scramble=scramble).numpy()
+        com = synth.planted_community(n, k, scramble=scramble).numpy()
+        assert com.min() == 0 and com.max() == (n - 1) // 256
+        same = (com[idx] == com[:, None]).mean()
+        assert 0.9 < same < 0.99, same
