@@ -32,6 +32,17 @@ inline void net_read(net_stream_t st, void* host, const void* dev, size_t bytes)
 inline void net_check_launches() { CU_TRY(cudaGetLastError()); }
 #endif
 
+// Test builds only (tests/cuda_emu, AddressSanitizer): every scratch piece is followed by a red zone and
+// only the pieces themselves are addressable, so a kernel that runs past its piece is reported.
+#ifdef GFICF_NET_ASAN
+#include <sanitizer/asan_interface.h>
+#define GFICF_NET_REDZONE 256
+#define GFICF_NET_PIECE(p, b) do { if (base) __asan_unpoison_memory_region((p), (b)); } while (0)
+#else
+#define GFICF_NET_REDZONE 0
+#define GFICF_NET_PIECE(p, b) do { } while (0)
+#endif
+
 namespace gficf {
 
 // number of bits needed for values in [0, max_value]
@@ -77,7 +88,8 @@ inline NetScratch net_scratch_layout(char* base, long long nn, long long cap) {
   size_t off = 0;
   auto take = [&](size_t b) {
     char* p = base + off;
-    off += (b + 255) / 256 * 256;
+    off += (b + GFICF_NET_REDZONE + 255) / 256 * 256;
+    GFICF_NET_PIECE(p, b);
     return p;
   };
   if (cap < nn) cap = nn;

@@ -13,9 +13,17 @@ struct Ctx {
   std::vector<char> scratch;
   unsigned flags = 0;
   NetCtx cx;
+  ~Ctx() {
+#ifdef GFICF_NET_ASAN
+    __asan_unpoison_memory_region(scratch.data(), scratch.size());
+#endif
+  }
   Ctx(long long nn, long long cap, int max_ctas) {
     scratch.assign(net_scratch_layout(nullptr, nn, cap).bytes, (char)0xA5);  // scratch is never assumed zero
     cx.st = 0;
+#ifdef GFICF_NET_ASAN
+    __asan_poison_memory_region(scratch.data(), scratch.size());  // the layout makes the pieces addressable again
+#endif
     cx.sc = net_scratch_layout(scratch.data(), nn, cap);
     cx.flags = &flags;
     cx.max_ctas = max_ctas;

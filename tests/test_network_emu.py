@@ -21,14 +21,17 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("emu") / "libnetwork_emu.so")
+def compile_emu(so, asan=False):
     cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-DGFICF_CUDA_EMU", "-I" + os.path.join(ROOT, "tests", "cuda_emu"),
-           "-I" + os.path.join(ROOT, "gficf_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-Wall", "-Werror",
-           os.path.join(ROOT, "tests", "cuda_emu", "network_emu.cpp"), "-o", so]
+           "-I" + os.path.join(ROOT, "gficf_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC",
+           "-Wall", "-Werror", os.path.join(ROOT, "tests", "cuda_emu", "network_emu.cpp"), "-o", so]
+    if asan:
+        cmd[1:1] = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-DGFICF_NET_ASAN"]
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+def load_emu(so):
     L = C.CDLL(so)
     L.emu_scan.argtypes = [_ip, C.c_longlong, _ll]
     L.emu_radix_sort.argtypes = [_ullp, _up, C.c_longlong, C.c_int, C.c_int]
@@ -43,6 +46,13 @@ def emu(tmp_path_factory):
                                  C.c_longlong, _dp, _dp, _dp, _ll, _up, C.c_int]
     L.emu_net_reduce.restype = C.c_longlong
     return L
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libnetwork_emu.so")
+    compile_emu(so)
+    return load_emu(so)
 
 
 def emu_build(L, node1, node2, w, nv, ctas=3):
@@ -353,3 +363,29 @@ def test_emulated_pipeline_matches_the_golden_vectors(emu):
         assert emu_quality(emu, red, cl2, nc2, res)[0] == float(g["quality2"])
         red2, _ = emu_reduce(emu, red, cl2, nc2)
         assert_same_network(red2, golden_network(g, "red2"))
+
+
+def test_emulated_kernels_under_address_sanitizer(tmp_path):
+    """The emulation doubles as a memory checker: the same kernels and launch sequences compiled with
+    -fsanitize=address, every scratch piece fenced by a poisoned red zone, outputs in exactly-sized
+    heap buffers -- an index that runs past its array is reported with the kernel's source line.
+    Runs in a child process (the sanitizer runtime has to be loaded first)."""
+    import shutil
+    import sys
+
+    libasan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not shutil.which("g++") or not os.path.isabs(libasan) or not os.path.exists(libasan):
+        pytest.skip("no AddressSanitizer runtime next to g++")
+    so = str(tmp_path / "libnetwork_emu_asan.so")
+    compile_emu(so, asan=True)
+    env = dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0:exitcode=23",
+               PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cuda_emu", "asan_run.py"), so],
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert "ERROR: AddressSanitizer" not in out.stderr, out.stderr[-4000:]
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-2000:])
+    assert "asan run ok" in out.stdout
+    # and the checker does see an overflow when there is one (an output array half the needed size)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cuda_emu", "asan_run.py"), so, "overflow"],
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert out.returncode != 0 and "heap-buffer-overflow" in out.stderr and "net_fill_kernel" in out.stderr
