@@ -76,8 +76,17 @@ class Network:
     def get_total_edge_weight(self) -> float:
         return float(self._total[0])
 
+    def _edge_ptrs(self):
+        """Pointers of neighbor / edge_weight; a network without edges (everything merged into self links)
+        has empty tensors, whose data pointer is null: the C entry points want a real address."""
+        if self.n_edges == 0:
+            dev = self.node_weight.device
+            self._dummy = (torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.float64, device=dev))
+            return self._dummy[0].data_ptr(), self._dummy[1].data_ptr()
+        return self.neighbor.data_ptr(), self.edge_weight.data_ptr()
+
     def _cluster_arg(self, cluster) -> torch.Tensor:
-        cl = torch.as_tensor(cluster, device=self.neighbor.device).to(torch.int32).contiguous()
+        cl = torch.as_tensor(cluster, device=self.node_weight.device).to(torch.int32).contiguous()
         if cl.shape != (self.n_nodes,):
             raise ValueError("one cluster id per node is required")
         return cl
@@ -90,9 +99,10 @@ class Network:
         q = torch.empty((1,), dtype=torch.float64, device=dev)
         flags = D.new_flags(dev)
         scratch = _scratch(dev, self.n_nodes, self.n_edges)
+        p_neighbor, p_edge_w = self._edge_ptrs()
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gficf_cuda_network_quality_dev(
-                self.first_neighbor_index.data_ptr(), self.neighbor.data_ptr(), self.edge_weight.data_ptr(),
+                self.first_neighbor_index.data_ptr(), p_neighbor, p_edge_w,
                 self.node_weight.data_ptr(), self.n_nodes, self.n_edges, cl.data_ptr(), nc, float(resolution),
                 self.total_edge_weight_self_links, self._total.data_ptr(), cw.data_ptr(), q.data_ptr(),
                 scratch.data_ptr(), scratch.numel(), flags.data_ptr(), D._stream_ptr()))
@@ -119,9 +129,10 @@ class Network:
         flags = D.new_flags(dev)
         scratch = _scratch(dev, self.n_nodes, self.n_edges)
         n_red = C.c_int64(0)
+        p_neighbor, p_edge_w = self._edge_ptrs()
         with torch.cuda.device(dev):
             _lib.check(L.gficf_cuda_network_reduce_dev(
-                self.first_neighbor_index.data_ptr(), self.neighbor.data_ptr(), self.edge_weight.data_ptr(),
+                self.first_neighbor_index.data_ptr(), p_neighbor, p_edge_w,
                 self.node_weight.data_ptr(), self.n_nodes, self.n_edges, cl.data_ptr(), nc,
                 self.total_edge_weight_self_links, r_first.data_ptr(),
                 r_neighbor.data_ptr(), r_edge_w.data_ptr(), cap, r_node_w.data_ptr(), scalars.data_ptr(),

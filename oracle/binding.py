@@ -313,6 +313,10 @@ class NetworkReference:
         L.ref_net_reduce.restype = C.c_void_p
         L.ref_net_free.argtypes = [C.c_void_p]
         L.ref_net_free.restype = None
+        L.ref_louvain_hooked.argtypes = [_ip, _ip, _dp, C.c_longlong, C.c_double, C.c_int, C.c_int, C.c_int,
+                                         C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p, _ip, _dp,
+                                         C.POINTER(C.c_longlong)]
+        L.ref_louvain_hooked.restype = C.c_int
 
     def _export(self, h) -> dict:
         nn, ne = C.c_int32(0), C.c_int32(0)
@@ -340,3 +344,77 @@ class NetworkReference:
 
     def free(self, net: dict) -> None:
         self.lib.ref_net_free(net.pop("handle"))
+
+    # -- the reference's Louvain run with the three bulk steps optionally supplied from outside --------
+    _HOOK_NETWORK = C.CFUNCTYPE(None, _ip, _ip, _dp, C.c_longlong, C.c_int, _ip, _ip, _dp, _dp, _dp)
+    _HOOK_QUALITY = C.CFUNCTYPE(C.c_double, C.c_int, _ip, _ip, _dp, _dp, C.c_double, _ip, C.c_int, C.c_double)
+    _HOOK_REDUCE = C.CFUNCTYPE(C.c_longlong, C.c_int, _ip, _ip, _dp, _dp, C.c_double, _ip, C.c_int, _ip, _ip, _dp,
+                               _dp, _dp)
+
+    def louvain(self, node1, node2, w, resolution=0.8, algorithm=1, n_start=10, n_iter=10, seed=180582, hooks=None):
+        """Labels (after orderClustersByNNodes), the maximum modularity and how often each hook ran.
+        `hooks` (optional) provides network(node1, node2, w, n_nodes) -> dict, quality(net, cluster,
+        n_clusters, resolution) -> float and reduce(net, cluster, n_clusters) -> dict on numpy arrays (`net`
+        dicts as everywhere in this module); without it the reference's own functions run: the
+        reference's algorithm end to end (RModularityOptimizer.cpp:101-172)."""
+        a, b, ww = _i32(node1), _i32(node2), _f64(w)
+        n_nodes = int(max(a.max(), b.max())) + 1
+        as_arr = np.ctypeslib.as_array
+        errors = []
+
+        def view_net(n, first, neighbor, edge_w, node_w, self_links):
+            f = as_arr(first, shape=(n + 1,))
+            e = int(f[n])
+            return dict(n_nodes=n, first=f, neighbor=as_arr(neighbor, shape=(max(e, 1),))[:e],
+                        edge_w=as_arr(edge_w, shape=(max(e, 1),))[:e], node_w=as_arr(node_w, shape=(n,)),
+                        self_links=self_links)
+
+        def cb_network(p1, p2, pw, m, n, first, neighbor, edge_w, node_w, total_w):
+            try:
+                net = hooks.network(as_arr(p1, shape=(m,)), as_arr(p2, shape=(m,)), as_arr(pw, shape=(m,)), n)
+                as_arr(first, shape=(n + 1,))[:] = net["first"]
+                as_arr(neighbor, shape=(2 * m,))[:] = net["neighbor"]
+                as_arr(edge_w, shape=(2 * m,))[:] = net["edge_w"]
+                as_arr(node_w, shape=(n,))[:] = net["node_w"]
+                total_w[0] = net["total_w"]
+            except Exception as ex:  # exceptions cannot cross the C frames
+                errors.append(ex)
+
+        def cb_quality(n, first, neighbor, edge_w, node_w, self_links, cluster, nc, res):
+            try:
+                return float(hooks.quality(view_net(n, first, neighbor, edge_w, node_w, self_links),
+                                           as_arr(cluster, shape=(n,)), nc, res))
+            except Exception as ex:
+                errors.append(ex)
+                return 0.0
+
+        def cb_reduce(n, first, neighbor, edge_w, node_w, self_links, cluster, nc, r_first, r_neighbor, r_edge_w,
+                      r_node_w, r_self_links):
+            try:
+                red = hooks.reduce(view_net(n, first, neighbor, edge_w, node_w, self_links),
+                                   as_arr(cluster, shape=(n,)), nc)
+                e = red["neighbor"].size
+                as_arr(r_first, shape=(nc + 1,))[:] = red["first"]
+                if e:
+                    as_arr(r_neighbor, shape=(e,))[:] = red["neighbor"]
+                    as_arr(r_edge_w, shape=(e,))[:] = red["edge_w"]
+                as_arr(r_node_w, shape=(nc,))[:] = red["node_w"]
+                r_self_links[0] = red["self_links"]
+                return e
+            except Exception as ex:
+                errors.append(ex)
+                return 0
+
+        keep = (self._HOOK_NETWORK(cb_network), self._HOOK_QUALITY(cb_quality), self._HOOK_REDUCE(cb_reduce))
+        ptrs = [C.cast(k, C.c_void_p) if hooks is not None else None for k in keep]
+        labels = np.zeros(n_nodes, np.int32)
+        max_mod = C.c_double(0.0)
+        calls = (C.c_longlong * 3)()
+        rc = self.lib.ref_louvain_hooked(_pi(a), _pi(b), _ptr(ww), a.size, float(resolution), int(algorithm),
+                                         int(n_start), int(n_iter), int(seed), ptrs[0], ptrs[1], ptrs[2],
+                                         _pi(labels), C.byref(max_mod), calls)
+        if errors:
+            raise errors[0]
+        if rc < 0:
+            raise RuntimeError("the reference's optimiser threw")
+        return labels, max_mod.value, list(calls)

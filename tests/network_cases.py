@@ -38,3 +38,53 @@ def assert_same_network(got, want):
     assert np.array_equal(got["node_w"], want["node_w"])
     assert got["self_links"] == want["self_links"]
     assert got["total_w"] == want["total_w"]
+
+
+class MirrorHooks:
+    """The three bulk steps of the Louvain run served by gficf_b200.modularity (the product's Python
+    mirror over the C ABI) for oracle.binding.NetworkReference.louvain: numpy in, numpy out.  `device`
+    is "cuda" on the GPU box; the CPU suite passes "cpu" with the emulated library patched in."""
+
+    def __init__(self, device):
+        import torch
+
+        from gficf_b200 import modularity
+
+        self.torch, self.modularity, self.device = torch, modularity, device
+        self.levels = 0
+
+    def _t(self, a, dtype):
+        return self.torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
+
+    def _net(self, d):
+        t = self.torch
+        net = self.modularity.Network(d["n_nodes"], self._t(d["first"], t.int64), self._t(d["neighbor"], t.int32),
+                                      self._t(d["edge_w"], t.float64), self._t(d["node_w"], t.float64), None,
+                                      d["self_links"])
+        return net
+
+    @staticmethod
+    def _dict(net):
+        return dict(n_nodes=net.n_nodes, first=net.first_neighbor_index.cpu().numpy(), neighbor=net.neighbor.cpu().numpy(),
+                    edge_w=net.edge_weight.cpu().numpy(), node_w=net.node_weight.cpu().numpy(),
+                    total_w=net.get_total_edge_weight(), self_links=net.total_edge_weight_self_links)
+
+    def network(self, node1, node2, w, n_nodes):
+        colptr, row = to_csc(node1, node2, n_nodes)
+        t = self.torch
+        self.top = self.modularity.matrix_to_network(self._t(colptr, t.int64), self._t(row, t.int32),
+                                                     self._t(w, t.float64))
+        return self._dict(self.top)
+
+    def quality(self, net, cluster, n_clusters, resolution):
+        # the optimiser evaluates the top-level network only: the device copy is still there
+        assert net["n_nodes"] == self.top.n_nodes
+        return self.top.calc_quality_function(cluster, resolution, n_clusters=n_clusters)
+
+    def reduce(self, net, cluster, n_clusters):
+        self.levels += 1
+        if net["n_nodes"] == self.top.n_nodes and net["neighbor"].size == self.top.n_edges:
+            src = self.top
+        else:  # a deeper level: the arrays come back from the optimiser; its total weight is not needed here
+            src = self._net(net)
+        return self._dict(src.create_reduced_network(cluster, n_clusters=n_clusters))

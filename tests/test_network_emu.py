@@ -389,3 +389,52 @@ def test_emulated_kernels_under_address_sanitizer(tmp_path):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cuda_emu", "asan_run.py"), so, "overflow"],
                          capture_output=True, text=True, env=env, timeout=900)
     assert out.returncode != 0 and "heap-buffer-overflow" in out.stderr and "net_fill_kernel" in out.stderr
+
+
+@pytest.mark.skipif(not NetworkReference.available(), reason="oracle/_ref not built")
+def test_louvain_labels_with_the_emulated_kernels_in_the_loop(emu, oracle, monkeypatch):
+    """End to end for row 3: the reference's own Louvain run (its runLocalMovingAlgorithm, JavaRandom,
+    mergeClusters -- oracle/ref_modopt_entry.cpp) with network construction, every reduced network and
+    every quality value supplied by this repository's kernels through gficf_b200.modularity: the labels
+    and the maximum modularity are those of the unmodified reference.  Also exercises a network
+    without edges (everything merged) through the Python mirror."""
+    import contextlib
+
+    import torch
+
+    from gficf_b200 import _lib, device as D, modularity, synth
+    from oracle import louvain
+    from tests.network_cases import MirrorHooks
+
+    for name in ("gficf_cuda_network_scratch_bytes", "gficf_cuda_network_dev", "gficf_cuda_network_quality_dev",
+                 "gficf_cuda_network_reduce_dev"):
+        res, args = _lib.PROTOTYPES[name]
+        getattr(emu, name).restype = res
+        getattr(emu, name).argtypes = args
+    monkeypatch.setattr(_lib, "lib", lambda: emu)
+    monkeypatch.setattr(D, "_require_cuda", lambda t, dtype: None)
+    monkeypatch.setattr(D, "_stream_ptr", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+
+    rel = oracle.parallel(synth.to_r_matrix(synth.knn_index(700, 8, family="planted", scramble=True)))
+    names, cols, rows, data = louvain.lower_triangle_edges(rel)
+    R = NetworkReference()
+    for algorithm in (1, 2):
+        want, q_want, _ = R.louvain(cols, rows, data, algorithm=algorithm, n_start=2, n_iter=3)
+        hooks = MirrorHooks("cpu")
+        got, q, calls = R.louvain(cols, rows, data, algorithm=algorithm, n_start=2, n_iter=3, hooks=hooks)
+        assert calls[0] == 1 and calls[1] >= 2 and calls[2] >= 2
+        assert np.array_equal(got, want) and q == q_want
+    if os.path.exists(louvain.MODOPT_BIN):  # and the driver restated around the hooks is the reference's own main loop
+        _, labels = louvain.louvain_labels(rel, algorithm=1, n_start=2, n_iter=3)
+        assert np.array_equal(R.louvain(cols, rows, data, algorithm=1, n_start=2, n_iter=3)[0], labels)
+    # a network whose edges all became self links still answers (null data pointers are not passed down)
+    top = hooks.top
+    merged = top.create_reduced_network(np.zeros(top.n_nodes, np.int32))
+    assert merged.n_edges == 0 and merged.n_nodes == 1
+    assert merged.calc_quality_function(np.zeros(1, np.int32), 0.01) == \
+        NetworkOracle().quality(dict(n_nodes=1, first=np.zeros(2, np.int32), neighbor=np.zeros(0, np.int32),
+                                     edge_w=np.zeros(0), node_w=merged.node_weight.numpy(), total_w=0.0,
+                                     self_links=merged.total_edge_weight_self_links), np.zeros(1, np.int32), 0.01)[0]
+    again = merged.create_reduced_network(np.zeros(1, np.int32))
+    assert again.n_edges == 0 and again.total_edge_weight_self_links == merged.total_edge_weight_self_links
