@@ -47,7 +47,6 @@ enum class St { Runnable, WaitCta, WaitWarp, Done };
 
 struct Fibre {
   ucontext_t ctx;
-  std::unique_ptr<char[]> stack;
   St st = St::Runnable;
   unsigned tid = 0;
 };
@@ -145,7 +144,9 @@ void launch(unsigned grid, unsigned block, F&& body) {
   CtaState cta;
   cta.body = body;
   cta.fibres.resize(block);
-  for (auto& f : cta.fibres) f.stack.reset(new char[kStackBytes]);
+  // fibre stacks are kept between launches (allocating 1024 x 64 KB per launch dominated the run time)
+  static std::vector<std::unique_ptr<char[]>> stack_pool;
+  while (stack_pool.size() < block) stack_pool.emplace_back(new char[kStackBytes]);
   cta.warps.resize(block / 32);
   g_cta = &cta;
   for (unsigned b = 0; b < grid; ++b) {
@@ -158,7 +159,7 @@ void launch(unsigned grid, unsigned block, F&& body) {
       f.st = St::Runnable;
       f.tid = t;
       getcontext(&f.ctx);
-      f.ctx.uc_stack.ss_sp = f.stack.get();
+      f.ctx.uc_stack.ss_sp = stack_pool[t].get();
       f.ctx.uc_stack.ss_size = kStackBytes;
       f.ctx.uc_link = nullptr;
       makecontext(&f.ctx, (void (*)())fibre_entry, 0);

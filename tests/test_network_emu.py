@@ -154,7 +154,7 @@ def test_emulated_sequential_sum_is_the_sequential_sum(emu):
         assert _emu_seq(emu, y)[1] & 32
 
 
-@pytest.mark.parametrize("nv,m,nc,seed", [(5, 6, 2, 1), (60, 300, 7, 2), (700, 6000, 40, 3), (1500, 9000, 300, 4),
+@pytest.mark.parametrize("nv,m,nc,seed", [(5, 6, 2, 1), (60, 300, 7, 2), (700, 6000, 40, 3), (1000, 5000, 200, 4),
                                            (300, 9000, 3, 5)])
 def test_emulated_network_pipeline_matches_oracle(emu, nv, m, nc, seed):
     rng = np.random.default_rng(seed)
