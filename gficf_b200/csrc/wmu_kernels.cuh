@@ -25,8 +25,14 @@
 // Sort: one CTA per gene, least-significant-digit radix sort (8-bit digits, 8 passes, passes whose
 // digit is constant are skipped) on order-preserving 64-bit keys with the element's original
 // position as payload, ping-pong buffers in global memory (L2 resident for typical N).
+// With GFICF_CUDA_EMU defined the header compiles as plain C++ against tests/cuda_emu/cuda_emu.h (the CPU test
+// suite runs both kernels that way); the product build never defines it.
 #pragma once
+#ifdef GFICF_CUDA_EMU
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace gficf {

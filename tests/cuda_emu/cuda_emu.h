@@ -275,6 +275,9 @@ inline T atomicAdd(T* p, T v) {
   *p = old + v;
   return old;
 }
+// mixed operand types as CUDA's overload set accepts them, e.g. atomicAdd(unsigned*, int)
+inline unsigned atomicAdd(unsigned* p, int v) { return atomicAdd<unsigned>(p, (unsigned)v); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned v) { return atomicAdd<unsigned long long>(p, v); }
 inline unsigned atomicOr(unsigned* p, unsigned v) {
   const unsigned old = *p;
   *p = old | v;
