@@ -73,13 +73,12 @@ struct NetScratch {
   long long* total;
   int* cnt;
   long long *ptr_a, *ptr_b;
-  double *dbl_a, *dbl_b;
+  double* dbl_b;  // (cw * cw) * resolution per cluster
   SeqState* seq_state;
   SeqFn* seq_fn;
   double* sums;  // [0] intra-cluster weight of calcQualityFunction
-  long long* ptr_c;
-  int* cnt_b;
-  long long n_tiles_cap;
+  long long* ptr_c;  // first traversal position of every node of the cluster-sorted list
+  int* cnt_b;        // its degree
   size_t bytes;
 };
 
@@ -95,7 +94,6 @@ inline NetScratch net_scratch_layout(char* base, long long nn, long long cap) {
   if (cap < nn) cap = nn;
   const long long n_tiles = (cap + kRadixTile - 1) / kRadixTile + 1;
   const long long scan_len = (256 * n_tiles > cap ? 256 * n_tiles : cap) + 1;
-  s.n_tiles_cap = n_tiles;
   for (int b = 0; b < 2; ++b) s.keys[b] = (unsigned long long*)take((size_t)cap * 8);
   for (int b = 0; b < 2; ++b) s.vals[b] = (unsigned*)take((size_t)cap * 4);
   s.aux = (unsigned*)take((size_t)cap * 4);
@@ -112,7 +110,6 @@ inline NetScratch net_scratch_layout(char* base, long long nn, long long cap) {
   s.cnt = (int*)take((size_t)(nn + 1) * 4);
   s.ptr_a = (long long*)take((size_t)(nn + 1) * 8);
   s.ptr_b = (long long*)take((size_t)(nn + 1) * 8);
-  s.dbl_a = (double*)take((size_t)(nn + 1) * 8);
   s.dbl_b = (double*)take((size_t)(nn + 1) * 8);
   s.seq_state = (SeqState*)take(sizeof(SeqState));
   s.seq_fn = (SeqFn*)take((size_t)kSeqMaxBlocks * sizeof(SeqFn));
