@@ -307,6 +307,74 @@ def run_traffic_probe(a):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def network_record(colptr, srows, sw, n, k, a, dev, flush):
+    """The bulk steps of the community detection on the device-resident graph: CSR
+    network, quality function, reduced network -- timed once each and, unless --no-parity, checked bit
+    for bit against the oracle (oracle/modopt_oracle.c, single-threaded like the reference)."""
+    import numpy as np
+    import torch
+
+    from gficf_b200 import modularity, synth
+
+    def once(fn):
+        flush.fill_(7)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res_ = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return res_, e0.elapsed_time(e1)
+
+    modularity.matrix_to_network(colptr, srows, sw)  # warm-up (allocator)
+    net, t_net = once(lambda: modularity.matrix_to_network(colptr, srows, sw))
+    nv = net.n_nodes
+    if nv == n and a.family == "planted":  # the planted communities (what a Louvain run converges towards)
+        cl = synth.planted_community(n, k, seed=a.seed, scramble=not a.no_scramble, device=dev).contiguous()
+        cl_what = "the planted communities"
+    else:
+        cl = (torch.arange(nv, device=dev, dtype=torch.int32) // 200).contiguous()
+        cl_what = "blocks of 200 vertices"
+    nc = int(cl.max()) + 1
+    res2 = 0.8 / (2 * net.get_total_edge_weight())  # resolution2 of RModularityOptimizer.cpp:101
+    q, t_q = once(lambda: net.calc_quality_function(cl, res2, n_clusters=nc))
+    red, t_red = once(lambda: net.create_reduced_network(cl, n_clusters=nc))
+    rec = {"network_ms": t_net, "quality_ms": t_q, "reduce_ms": t_red, "vertices": nv,
+           "directed_edges": net.n_edges, "clusters": nc, "reduced_edges": red.n_edges, "quality": q,
+           "what": "matrixToNetwork / calcQualityFunction / createReducedNetwork "
+                   "(src/ModularityOptimizer.cpp:761-806, :462-482, :322-373) on the device-resident graph, "
+                   "clustering = " + cl_what + "; the local moving loop itself stays on the host"}
+    if not a.no_parity:
+        from oracle.binding import NetworkOracle
+
+        orc = NetworkOracle()
+        cols = np.repeat(np.arange(nv, dtype=np.int32), np.diff(colptr.cpu().numpy()))
+        t0 = time.perf_counter()
+        want = orc.network(cols, srows.cpu().numpy(), sw.cpu().numpy())
+        t1 = time.perf_counter()
+        cl_h = cl.cpu().numpy()
+        q_want, _ = orc.quality(want, cl_h, res2)
+        t2 = time.perf_counter()
+        red_want = orc.reduce(want, cl_h)
+        t3 = time.perf_counter()
+        rec["cpu_ms"] = {"network": (t1 - t0) * 1e3, "quality": (t2 - t1) * 1e3, "reduce": (t3 - t2) * 1e3,
+                         "cores": 1, "kind": "port"}
+
+        def same(x, d):
+            return bool(np.array_equal(x.first_neighbor_index.cpu().numpy(), d["first"]) and
+                        np.array_equal(x.neighbor.cpu().numpy(), d["neighbor"]) and
+                        np.array_equal(x.edge_weight.cpu().numpy(), d["edge_w"]) and
+                        np.array_equal(x.node_weight.cpu().numpy(), d["node_w"]))
+
+        rec["parity"] = {"network_arrays_equal": same(net, want),
+                         "total_edge_weight_equal": bool(net.get_total_edge_weight() == want["total_w"]),
+                         "quality_equal": bool(q == q_want),
+                         "reduced_arrays_equal": same(red, red_want),
+                         "self_links_equal": bool(red.total_edge_weight_self_links == red_want["self_links"])}
+    del net, red
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -686,73 +754,12 @@ def run_ours(a):
         except Exception as ex:  # an extra record, never a reason to lose the bench line
             snn_rec = {"error": str(ex)[:200]}
 
-    # ---- and the bulk steps of the community detection on that graph: CSR network,
-    #      quality function, reduced network -- timed once each, checked bit for bit against the oracle
+    # ---- and the bulk steps of the community detection on that graph
     net_rec = None
     if snn_rec is not None and "error" not in snn_rec:
         try:
-            from gficf_b200 import modularity
-
-            def once(fn):
-                flush.fill_(7)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                res_ = fn()
-                e1.record()
-                torch.cuda.synchronize()
-                return res_, e0.elapsed_time(e1)
-
-            modularity.matrix_to_network(colptr, srows, sw)  # warm-up (allocator)
-            net, t_net = once(lambda: modularity.matrix_to_network(colptr, srows, sw))
-            nv_ = net.n_nodes
-            if nv_ == n and a.family == "planted":  # the planted communities (what a Louvain run converges towards)
-                cl = synth.planted_community(n, k, seed=a.seed, scramble=not a.no_scramble, device=dev).contiguous()
-                cl_what = "the planted communities"
-            else:
-                cl = (torch.arange(nv_, device=dev, dtype=torch.int32) // 200).contiguous()
-                cl_what = "blocks of 200 vertices"
-            nc_ = int(cl.max()) + 1
-            res2 = 0.8 / (2 * net.get_total_edge_weight())  # resolution2 of RModularityOptimizer.cpp:101
-            q_, t_q = once(lambda: net.calc_quality_function(cl, res2, n_clusters=nc_))
-            red, t_red = once(lambda: net.create_reduced_network(cl, n_clusters=nc_))
-            net_rec = {"network_ms": t_net, "quality_ms": t_q, "reduce_ms": t_red, "vertices": nv_,
-                       "directed_edges": net.n_edges, "clusters": nc_, "reduced_edges": red.n_edges, "quality": q_,
-                       "what": "matrixToNetwork / calcQualityFunction / createReducedNetwork "
-                               "(src/ModularityOptimizer.cpp:761-806, :462-482, :322-373) on the device-resident graph, "
-                               "clustering = " + cl_what + "; the local moving loop itself stays on the host"}
-            if not a.no_parity:
-                from oracle.binding import NetworkOracle
-
-                O_ = NetworkOracle()
-                cols_ = np.repeat(np.arange(nv_, dtype=np.int32), np.diff(colptr.cpu().numpy()))
-                t0_ = time.perf_counter()
-                want = O_.network(cols_, srows.cpu().numpy(), sw.cpu().numpy())
-                t1_ = time.perf_counter()
-                cl_h = cl.cpu().numpy()
-                q_want, _ = O_.quality(want, cl_h, res2)
-                t2_ = time.perf_counter()
-                red_want = O_.reduce(want, cl_h)
-                t3_ = time.perf_counter()
-                net_rec["cpu_ms"] = {"network": (t1_ - t0_) * 1e3, "quality": (t2_ - t1_) * 1e3,
-                                     "reduce": (t3_ - t2_) * 1e3, "cores": 1, "kind": "port"}
-                net_rec["parity"] = {
-                    "network_arrays_equal": bool(
-                        np.array_equal(net.first_neighbor_index.cpu().numpy(), want["first"]) and
-                        np.array_equal(net.neighbor.cpu().numpy(), want["neighbor"]) and
-                        np.array_equal(net.edge_weight.cpu().numpy(), want["edge_w"]) and
-                        np.array_equal(net.node_weight.cpu().numpy(), want["node_w"])),
-                    "total_edge_weight_equal": bool(net.get_total_edge_weight() == want["total_w"]),
-                    "quality_equal": bool(q_ == q_want),
-                    "reduced_arrays_equal": bool(
-                        np.array_equal(red.first_neighbor_index.cpu().numpy(), red_want["first"]) and
-                        np.array_equal(red.neighbor.cpu().numpy(), red_want["neighbor"]) and
-                        np.array_equal(red.edge_weight.cpu().numpy(), red_want["edge_w"]) and
-                        np.array_equal(red.node_weight.cpu().numpy(), red_want["node_w"])),
-                    "self_links_equal": bool(red.total_edge_weight_self_links == red_want["self_links"])}
-                del want, red_want, cols_
-            del net, red, cl
-            torch.cuda.empty_cache()
-        except Exception as ex:
+            net_rec = network_record(colptr, srows, sw, n, k, a, dev, flush)
+        except Exception as ex:  # an extra record, never a reason to lose the bench line
             net_rec = {"error": str(ex)[:200]}
     colptr = srows = sw = None
 
