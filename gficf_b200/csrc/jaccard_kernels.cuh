@@ -27,6 +27,7 @@
 //     from/to/w with coalesced streaming stores (st.global.cs) so that the
 //     output does not evict the index matrix from L2.
 #pragma once
+#include "jaccard_weight.cuh"
 #include "scan_kernels.cuh"
 
 // tuning knobs (overridable with -D for A/B runs; defaults are the measured best)
@@ -112,12 +113,6 @@ __device__ __forceinline__ void probe4(unsigned& acc, unsigned tbl32, unsigned m
     add_if_eq<INC * 0x80u>(acc, x2, self);
     add_if_eq<INC * 0x80u>(acc, x3, self);
   }
-}
-
-__device__ __forceinline__ double jaccard_weight(int u, int k) {
-  // rcpp_parallel_jaccard_coeff.cpp:51  u/(2.0*mat.ncol() - u) : exact integer
-  // operands, ONE IEEE-754 double division (correctly rounded on the device too).
-  return __ddiv_rn((double)u, 2.0 * (double)k - (double)u);
 }
 
 // ---------------------------------------------------------------------------

@@ -13,6 +13,13 @@
 #endif
 #include <stdint.h>
 
+// dynamic shared memory of a kernel: `extern __shared__` on the device, a per-launch buffer in the emulation
+#ifdef GFICF_CUDA_EMU
+#define GFICF_DYNAMIC_SMEM(name) unsigned char* name = cuda_emu::dynamic_smem()
+#else
+#define GFICF_DYNAMIC_SMEM(name) extern __shared__ unsigned char name[]
+#endif
+
 namespace gficf {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;

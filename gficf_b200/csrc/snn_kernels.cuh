@@ -22,8 +22,10 @@
 // undirected pair {i,t} carries w (one direction) or w + w (both), and the direction that emits it
 // is: the one from the smaller vertex id if both exist, else the only one.
 // Supported domain (flags otherwise): k <= 127, no repeated ids.
+// PTX-free: with GFICF_CUDA_EMU the header compiles as plain C++ (tests/test_snn_emu.py runs the kernels that way).
 #pragma once
-#include "jaccard_kernels.cuh"
+#include "jaccard_weight.cuh"
+#include "scan_kernels.cuh"
 
 namespace gficf {
 
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(256)
 snn_sort_big_kernel(const long long* __restrict__ colptr, const SnnEntry* __restrict__ tmp,
                     int* __restrict__ row_out, double* __restrict__ w_out, const int* __restrict__ big_cols,
                     const int* __restrict__ n_big) {
-  extern __shared__ unsigned char snn_smem[];
+  GFICF_DYNAMIC_SMEM(snn_smem);
   int* s_row = reinterpret_cast<int*>(snn_smem);                            // [kSnnSmemSortMax]
   double* s_w = reinterpret_cast<double*>(snn_smem + kSnnSmemSortMax * 4);  // [kSnnSmemSortMax]
   const int nb = *n_big;

@@ -68,6 +68,8 @@ struct CtaState {
 
 inline CtaState* g_cta = nullptr;
 inline long long g_launches = 0;
+inline std::vector<unsigned char> g_dyn_smem;  // the launch's dynamic shared memory (CTAs run one at a time)
+inline unsigned char* dynamic_smem() { return g_dyn_smem.data(); }
 
 [[noreturn]] inline void die(const char* msg) {
   fprintf(stderr, "cuda_emu: %s\n", msg);
@@ -136,7 +138,8 @@ constexpr size_t kStackBytes = 64 * 1024;
 
 // run `body` (a call of the kernel function with its arguments) for grid x block threads
 template <class F>
-void launch(unsigned grid, unsigned block, F&& body) {
+void launch(unsigned grid, unsigned block, F&& body, size_t dynamic_smem_bytes = 0) {
+  g_dyn_smem.assign(dynamic_smem_bytes + 16, (unsigned char)0xA5);
   if (block == 0 || block % 32 != 0 || block > 1024) die("block size must be a multiple of 32, at most 1024");
   ++g_launches;
   gridDim = Dim3{grid, 1, 1};
