@@ -70,8 +70,12 @@ __device__ __forceinline__ int4 ldg_row(const char* lane_base, unsigned t, unsig
 // acc += INC when the table slot of x holds x: ISETP + predicated IADD, no select chain
 template <unsigned INC>
 __device__ __forceinline__ void add_if_eq(unsigned& acc, unsigned a, unsigned b) {
+#ifdef GFICF_CUDA_EMU
+  if (a == b) acc += INC;
+#else
   asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}"
       : "+r"(acc) : "r"(a), "r"(b), "n"(INC));
+#endif
 }
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) {
@@ -79,18 +83,26 @@ __device__ __forceinline__ unsigned smem_addr(const void* p) {
 }
 
 __device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+#ifdef GFICF_CUDA_EMU
+  return *static_cast<const unsigned*>(cuda_emu::smem_ptr(addr));
+#else
   unsigned r;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
   return r;
+#endif
 }
 
 // shared address of the table slot of id x: IMAD (multiplicative hash), SHF (top bits), and one
 // IMAD for base + 4*slot (kept opaque, otherwise it is split into a mask and an add)
 template <int SHIFT>
 __device__ __forceinline__ unsigned slot_addr(unsigned tbl32, unsigned x, unsigned mult) {
+#ifdef GFICF_CUDA_EMU
+  return ((x * mult) >> SHIFT) * 4u + tbl32;
+#else
   unsigned a;
   asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"((x * mult) >> SHIFT), "r"(tbl32));
   return a;
+#endif
 }
 
 // membership probes of the 4 ids of one 16-byte piece against a collision-free table at
@@ -151,7 +163,7 @@ __global__ void __launch_bounds__(kLayoutThreads)
 layout_colmajor_kernel(const T* __restrict__ src, long long ld_rows, long long ld_row0, long long n,
                   int k, int kp, long long row_lo, long long row_hi, int* __restrict__ dst,
                   unsigned* __restrict__ flags, int tile_r) {
-  extern __shared__ int tile[];  // [tile_r][kp + 1]
+  GFICF_DYNAMIC_SMEM_T(int, tile);  // [tile_r][kp + 1]
   const int tid = threadIdx.x;
   const int stride = kp + 1;
   const long long ntiles = (row_hi - row_lo + tile_r - 1) / tile_r;
@@ -493,7 +505,7 @@ jaccard_wide_k_kernel(const int* __restrict__ idx, int k, int kp, long long row_
   constexpr int TS = 1 << LOG_TS, SHIFT = 32 - LOG_TS;
   constexpr bool COUNTS_ONLY = OUT != 0;
   constexpr bool MUT = OUT == 2;  // needs k <= 127 (bit 7 of the count byte)
-  extern __shared__ unsigned smem_u[];
+  GFICF_DYNAMIC_SMEM_T(unsigned, smem_u);
   unsigned* tbl = smem_u;                             // [TS]
   int* srow_base = reinterpret_cast<int*>(tbl + TS);   // [2][128] ids of row i
   int* scnt_base = srow_base + 256;                    // [2][128] u per edge
@@ -657,7 +669,7 @@ jaccard_large_k_kernel(const int* __restrict__ idx, int k, int kp, long long row
                        double* __restrict__ o_from, double* __restrict__ o_to,
                        double* __restrict__ o_w, CT* __restrict__ o_u, unsigned* __restrict__ flags) {
   constexpr int TS = 1 << kLargeLogTs, SHIFT = 32 - kLargeLogTs;
-  extern __shared__ unsigned smem_u[];
+  GFICF_DYNAMIC_SMEM_T(unsigned, smem_u);
   unsigned* tbl = smem_u;                                              // [TS]
   int* srow = reinterpret_cast<int*>(tbl + TS);                         // [1024] ids of row i
   unsigned short* scnt = reinterpret_cast<unsigned short*>(srow + kLargeMaxK);  // [1024] u per edge
@@ -838,9 +850,13 @@ struct StreamSegs {
 };
 
 __device__ __forceinline__ unsigned ld_volatile_u8(const uint8_t* p) {
+#ifdef GFICF_CUDA_EMU
+  return *static_cast<const volatile uint8_t*>(p);
+#else
   unsigned v;
   asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
+#endif
 }
 
 #ifndef GFICF_STREAM_BATCH
@@ -864,9 +880,13 @@ __device__ __forceinline__ void stream_store(V* p, V v) {
 }
 
 __device__ __forceinline__ unsigned ld_volatile_u16(const uint8_t* p) {
+#ifdef GFICF_CUDA_EMU
+  return *reinterpret_cast<const volatile unsigned short*>(p);
+#else
   unsigned short v;
   asm volatile("ld.volatile.global.u16 %0, [%1];" : "=h"(v) : "l"(p));
   return v;
+#endif
 }
 
 // W = edges per thread and round that are adjacent in memory: 1 (8-byte stores) or 2 (one 16-bit

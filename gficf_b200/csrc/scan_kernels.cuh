@@ -15,10 +15,11 @@
 
 // dynamic shared memory of a kernel: `extern __shared__` on the device, a per-launch buffer in the emulation
 #ifdef GFICF_CUDA_EMU
-#define GFICF_DYNAMIC_SMEM(name) unsigned char* name = cuda_emu::dynamic_smem()
+#define GFICF_DYNAMIC_SMEM_T(type, name) type* name = reinterpret_cast<type*>(cuda_emu::dynamic_smem())
 #else
-#define GFICF_DYNAMIC_SMEM(name) extern __shared__ unsigned char name[]
+#define GFICF_DYNAMIC_SMEM_T(type, name) extern __shared__ type name[]
 #endif
+#define GFICF_DYNAMIC_SMEM(name) GFICF_DYNAMIC_SMEM_T(unsigned char, name)
 
 namespace gficf {
 

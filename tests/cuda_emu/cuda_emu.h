@@ -68,8 +68,11 @@ struct CtaState {
 
 inline CtaState* g_cta = nullptr;
 inline long long g_launches = 0;
-inline std::vector<unsigned char> g_dyn_smem;  // the launch's dynamic shared memory (CTAs run one at a time)
-inline unsigned char* dynamic_smem() { return g_dyn_smem.data(); }
+// the launch's dynamic shared memory (CTAs run one at a time); static so that it lies inside the 32-bit
+// window of emulated shared-memory addresses (smem_base below), like the kernels' static __shared__ arrays
+constexpr size_t kMaxDynamicSmem = 232 * 1024;
+alignas(128) inline unsigned char g_dyn_smem[kMaxDynamicSmem];
+inline unsigned char* dynamic_smem() { return g_dyn_smem; }
 
 [[noreturn]] inline void die(const char* msg) {
   fprintf(stderr, "cuda_emu: %s\n", msg);
@@ -139,7 +142,8 @@ constexpr size_t kStackBytes = 64 * 1024;
 // run `body` (a call of the kernel function with its arguments) for grid x block threads
 template <class F>
 void launch(unsigned grid, unsigned block, F&& body, size_t dynamic_smem_bytes = 0) {
-  g_dyn_smem.assign(dynamic_smem_bytes + 16, (unsigned char)0xA5);
+  if (dynamic_smem_bytes > kMaxDynamicSmem) die("more dynamic shared memory than an SM has");
+  memset(g_dyn_smem, 0xA5, dynamic_smem_bytes);
   if (block == 0 || block % 32 != 0 || block > 1024) die("block size must be a multiple of 32, at most 1024");
   ++g_launches;
   gridDim = Dim3{grid, 1, 1};
@@ -281,6 +285,11 @@ inline T atomicAdd(T* p, T v) {
 // mixed operand types as CUDA's overload set accepts them, e.g. atomicAdd(unsigned*, int)
 inline unsigned atomicAdd(unsigned* p, int v) { return atomicAdd<unsigned>(p, (unsigned)v); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned v) { return atomicAdd<unsigned long long>(p, v); }
+inline unsigned atomicCAS(unsigned* p, unsigned expected, unsigned desired) {
+  const unsigned old = *p;
+  if (old == expected) *p = desired;
+  return old;
+}
 inline unsigned atomicOr(unsigned* p, unsigned v) {
   const unsigned old = *p;
   *p = old | v;
@@ -312,3 +321,34 @@ inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return 
 inline double __dsqrt_rn(double a) { volatile double r = std::sqrt(a); return r; }
 inline long long __double_as_longlong(double v) { return cuda_emu::from_raw<long long>(cuda_emu::to_raw(v)); }
 inline double __longlong_as_double(long long v) { return cuda_emu::from_raw<double>(cuda_emu::to_raw(v)); }
+
+// ---- vector types, cache-hinted accesses, fences (what jaccard_kernels.cuh uses) ----------------
+struct __attribute__((aligned(8))) int2 { int x, y; };
+struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
+struct __attribute__((aligned(16))) double2 { double x, y; };
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline void __stcs(T* p, T v) { *p = v; }
+template <class T> inline void __stcg(T* p, T v) { *p = v; }
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline void __nanosleep(unsigned) {}
+inline long long clock64() { return 0; }
+template <class T> inline T min(T a, T b) { return b < a ? b : a; }
+template <class T> inline T max(T a, T b) { return a < b ? b : a; }
+inline long long min(long long a, int b) { return b < a ? b : a; }
+inline long long min(int a, long long b) { return b < a ? b : a; }
+// shared-memory "addresses": 32-bit offsets from a fixed base below the library's static data
+namespace cuda_emu {
+inline char g_smem_anchor = 0;
+inline uintptr_t smem_base() { return (uintptr_t)&g_smem_anchor - (1ull << 31); }
+inline void* smem_ptr(unsigned addr) { return (void*)(smem_base() + addr); }
+}  // namespace cuda_emu
+inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)((uintptr_t)p - cuda_emu::smem_base()); }
