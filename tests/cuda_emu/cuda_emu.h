@@ -141,12 +141,12 @@ constexpr size_t kStackBytes = 64 * 1024;
 
 // run `body` (a call of the kernel function with its arguments) for grid x block threads
 template <class F>
-void launch(unsigned grid, unsigned block, F&& body, size_t dynamic_smem_bytes = 0) {
+void launch(unsigned grid, unsigned block, F&& body, size_t dynamic_smem_bytes = 0, unsigned grid_y = 1) {
   if (dynamic_smem_bytes > kMaxDynamicSmem) die("more dynamic shared memory than an SM has");
   memset(g_dyn_smem, 0xA5, dynamic_smem_bytes);
   if (block == 0 || block % 32 != 0 || block > 1024) die("block size must be a multiple of 32, at most 1024");
   ++g_launches;
-  gridDim = Dim3{grid, 1, 1};
+  gridDim = Dim3{grid, grid_y, 1};
   blockDim = Dim3{block, 1, 1};
   CtaState cta;
   cta.body = body;
@@ -156,8 +156,9 @@ void launch(unsigned grid, unsigned block, F&& body, size_t dynamic_smem_bytes =
   while (stack_pool.size() < block) stack_pool.emplace_back(new char[kStackBytes]);
   cta.warps.resize(block / 32);
   g_cta = &cta;
+  for (unsigned by = 0; by < grid_y; ++by)
   for (unsigned b = 0; b < grid; ++b) {
-    blockIdx = Idx3{b, 0, 0};
+    blockIdx = Idx3{b, by, 0};
     cta.live = block;
     cta.cta_arrived = 0;
     for (auto& w : cta.warps) w.arrived = 0;

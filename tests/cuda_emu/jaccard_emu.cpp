@@ -104,6 +104,9 @@ extern "C" {
 //       2 counts + compaction (serial export; counts must come with set semantics: exact kernel);
 //       3 exact kernel (multiset) + expand; 4 counts with the mutual bit (returned in `counts`, no expand);
 //       5 tagged counts, grouped stores (k <= 32; returned in `counts`)
+//       6 / 7 the two halves of the multi-GPU gather on one "device": parity-tagged counts (6: row stores,
+//         7: grouped stores, k <= 32) into `counts`, then expand_stream_kernel over three row segments
+//         reading them (every byte is already there, so nothing spins); k <= 127
 // idx_colmajor: n x k doubles (1-based); out_colmajor: (n*k) x 3.  Returns the flags, or 0x80000000 when
 // the fast kernels do not cover k in that mode.
 unsigned emu_jaccard(const double* idx_colmajor, long long n, int k, int mode, double* out_colmajor,
@@ -145,6 +148,24 @@ unsigned emu_jaccard(const double* idx_colmajor, long long n, int k, int mode, d
     ok = fast<2>(d_idx, k, 0, n, nullptr, nullptr, nullptr, counts, d_flags, 0, grid);
   } else if (mode == 5) {
     ok = fast<3>(d_idx, k, 0, n, nullptr, nullptr, nullptr, counts, d_flags, 0x80u, grid);
+  }
+  else if (mode == 6 || mode == 7) {
+    if (k > 127 || (mode == 7 && k > 32)) return 0x80000000u;
+    const unsigned tag = 0x80u;
+    ok = mode == 7 ? fast<3>(d_idx, k, 0, n, nullptr, nullptr, nullptr, counts, d_flags, tag, grid)
+                   : fast<1>(d_idx, k, 0, n, nullptr, nullptr, nullptr, counts, d_flags, tag, grid);
+    StreamSegs segs;
+    const long long cut1 = (n / 3) & ~1LL, cut2 = (2 * n / 3) & ~1LL;  // even rows: even first edges for any k
+    segs.lo[0] = 0, segs.hi[0] = cut1, segs.lo[1] = cut1, segs.hi[1] = cut2, segs.lo[2] = cut2, segs.hi[2] = n;
+    const bool pair = (((uintptr_t)f | (uintptr_t)t | (uintptr_t)w) & 15) == 0 && ((uintptr_t)counts & 1) == 0;
+    const unsigned char* cu = counts;
+    if (pair) {
+      cuda_emu::launch(2, kExpandThreads, [=] { expand_stream_kernel<2>(d_idx, k, kp, segs, cu, f, t, w, tag, 1LL << 40, d_flags); },
+                       0, 3);
+    } else {
+      cuda_emu::launch(2, kExpandThreads, [=] { expand_stream_kernel<1>(d_idx, k, kp, segs, cu, f, t, w, tag, 1LL << 40, d_flags); },
+                       0, 3);
+    }
   }
   return ok ? flags : 0x80000000u;
 }

@@ -85,6 +85,10 @@ def test_emulated_fast_kernels_match_oracle(emu, oracle, n, k):
     if k <= 32:  # parity-tagged counts, rows sent in groups of 8 (the multi-GPU gather's peer kernel)
         _, ut, _, flags = run(emu, idx, 5)
         assert flags == 0 and np.array_equal(ut, u | 0x80)
+    if k <= 127:  # both halves of the streaming gather: tagged counts, then the expand that reads (polls) them
+        for mode in (6, 7) if k <= 32 else (6,):
+            out, ut, _, flags = run(emu, idx, mode)
+            assert flags == 0 and np.array_equal(ut, u | 0x80) and np.array_equal(out, want), mode
 
 
 def test_emulated_layout_flags_bad_ids(emu):
