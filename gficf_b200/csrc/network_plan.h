@@ -249,9 +249,8 @@ inline void net_quality(const NetCtx& cx, const long long* first, const int* nei
 // entries), r_node_w[n_clusters], r_self_links[1] = totalEdgeWeightSelfLinks of the reduced network
 // (the parent's value `self_links` plus, in traversal order, every edge that stays inside a cluster,
 // :329/:351), r_total_w[1] = getTotalEdgeWeight of the reduced network.  Returns the number of
-// reduced edges, or -1 when
-// r_cap is too small (*n_needed then holds the number).  Synchronises the stream (entry counts and
-// the sequential sums are read back).
+// reduced edges, or -1 when r_cap is too small (*n_needed then holds the number).  Synchronises the
+// stream (entry counts and the positions of the sequential sums are read back).
 inline long long net_reduce(const NetCtx& cx, const long long* first, const int* neighbor, const double* edge_w,
                             const double* node_w, long long n_nodes, long long n_edges, const int* cluster,
                             int n_clusters, double self_links, long long* r_first, int* r_neighbor,
@@ -301,7 +300,6 @@ inline long long net_reduce(const NetCtx& cx, const long long* first, const int*
   net_seq_sum(cx, r_edge_w, n_seg, 0.0, 0.5, r_total_w);
   return n_seg;
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // bodies of the C entry points gficf_cuda_network_*_dev (argument checks included, so that the
