@@ -110,3 +110,26 @@ def test_host_expand_writes_the_reference_rows(oracle):
         assert (out[:lo * k] == -3.0).all() and (out[hi * k:] == -3.0).all()
     bad = np.zeros(4)
     assert L.gficf_cuda_expand_host(bad.ctypes.data, 2, 2, 2, bad.ctypes.data, 0, 2, bad.ctypes.data, 1) == 1
+
+
+def test_product_build_never_enables_the_emulation():
+    """GFICF_CUDA_EMU (plain-C++ bodies of the kernels for tests/cuda_emu) is a test-only switch: no build
+    recipe of the product defines it, no product source includes the emulation header outside that switch,
+    and the shipped library carries nothing of it."""
+    import subprocess
+
+    recipes = [os.path.join(ROOT, "gficf_b200", "csrc", "Makefile"), os.path.join(ROOT, "gficf_b200", "rpkg", "src", "Makevars.cuda"),
+               os.path.join(ROOT, "tools", "stage_rpkg.sh"), os.path.join(ROOT, "__graft_entry__.py"),
+               os.path.join(ROOT, "gficf_b200", "_lib.py")]
+    for p in recipes:
+        assert "GFICF_CUDA_EMU" not in open(p).read(), p
+        assert "cuda_emu" not in open(p).read(), p
+    csrc = os.path.join(ROOT, "gficf_b200", "csrc")
+    for name in os.listdir(csrc):
+        if name.endswith((".cu", ".cuh", ".h", ".cpp")):
+            lines = open(os.path.join(csrc, name)).read().splitlines()
+            for i, line in enumerate(lines):
+                if '#include "cuda_emu.h"' in line:
+                    assert "#ifdef GFICF_CUDA_EMU" in lines[i - 1], (name, i)
+    syms = subprocess.run(["nm", "-D", "--defined-only", gficf_b200.library_path()], capture_output=True, text=True).stdout
+    assert "cuda_emu" not in syms and "emu_" not in syms
