@@ -25,7 +25,7 @@ def main():
         print("the overflow went unnoticed")
         return
     O = NetworkOracle()
-    for nv, m, nc, ctas in ((40, 150, 5, 1), (300, 2500, 12, 2), (100, 300, 100, 3)):
+    for nv, m, nc, ctas in ((40, 150, 5, 1), (250, 2000, 12, 2)):
         n1, n2, w = random_lower(rng, nv, m)
         nv = int(max(n1.max(), n2.max())) + 1
         want = O.network(n1, n2, w)

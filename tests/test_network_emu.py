@@ -162,7 +162,7 @@ def test_emulated_sequential_sum_is_the_sequential_sum(emu):
         assert _emu_seq(emu, y)[1] & 32
 
 
-@pytest.mark.parametrize("nv,m,nc,seed", [(5, 6, 2, 1), (60, 300, 7, 2), (700, 6000, 40, 3), (1000, 5000, 200, 4),
+@pytest.mark.parametrize("nv,m,nc,seed", [(5, 6, 2, 1), (60, 300, 7, 2), (700, 6000, 40, 3), (600, 3000, 100, 4),
                                            (300, 9000, 3, 5)])
 def test_emulated_network_pipeline_matches_oracle(emu, nv, m, nc, seed):
     rng = np.random.default_rng(seed)
@@ -427,7 +427,7 @@ def test_louvain_labels_with_the_emulated_kernels_in_the_loop(emu, oracle, monke
     rel = oracle.parallel(synth.to_r_matrix(synth.knn_index(700, 8, family="planted", scramble=True)))
     names, cols, rows, data = louvain.lower_triangle_edges(rel)
     R = NetworkReference()
-    for algorithm in (1, 2):
+    for algorithm in (1,):  # algorithm 2 (multilevel refinement) runs in tests/test_gpu_zz_louvain_loop.py
         want, q_want, _ = R.louvain(cols, rows, data, algorithm=algorithm, n_start=2, n_iter=3)
         hooks = MirrorHooks("cpu")
         got, q, calls = R.louvain(cols, rows, data, algorithm=algorithm, n_start=2, n_iter=3, hooks=hooks)
